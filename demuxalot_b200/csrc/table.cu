@@ -1,0 +1,159 @@
+// Regularised betas (demux.py:367-390) and the per-SNP normalised probability table (demux.py:267-274).
+//
+// Both are small streaming kernels over the [V, G] float32 betas: HBM-bound, 12 bytes per element for the
+// table (read betas, read addition, write P).  All SNP sums are float64 and are taken over the SNP's
+// variants in ascending variant id, which is the order np.bincount adds them in, so results are bit-exact.
+#include "common.cuh"
+
+namespace dmx {
+
+// numpy's float32 pairwise summation (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum) as used by
+// `betas.sum(axis=1)` at demux.py:383: 8 interleaved accumulators for n <= 128, recursive halving above.
+__device__ float np_pairwise_sum_f32(const float* __restrict__ a, int n) {
+    if (n < 8) {
+        float res = 0.f;
+        for (int i = 0; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    if (n <= 128) {
+        float r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = a[k];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r[k] = __fadd_rn(r[k], a[i + k]);
+        }
+        float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                              __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < n; ++i) res = __fadd_rn(res, a[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return __fadd_rn(np_pairwise_sum_f32(a, n2), np_pairwise_sum_f32(a + n2, n - n2));
+}
+
+__global__ void rowsum_kernel(const float* __restrict__ betas, int64_t ld, int64_t n_variants, int n_genotypes,
+                              float* __restrict__ rowsum) {
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < n_variants;
+         v += (int64_t)gridDim.x * blockDim.x) {
+        rowsum[v] = __fadd_rn(0.f, np_pairwise_sum_f32(betas + v * ld, n_genotypes));
+    }
+}
+
+// one thread per SNP: float64 sums over its variants, then the per-variant prior addition (float32)
+__global__ void prior_addition_kernel(const float* rowsum, const int32_t* __restrict__ snp_offsets,
+                                      const int32_t* __restrict__ snp_variants, int64_t n_snps,
+                                      const int64_t* __restrict__ n_mol, double default_prior,
+                                      float* addition /* may alias rowsum: a thread writes only its own SNP's
+                                                         variants, each after its last read */) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n_snps; s += (int64_t)gridDim.x * blockDim.x) {
+        const int lo = snp_offsets[s], hi = snp_offsets[s + 1];
+        double sum_betas = 0.0, sum_mol = 0.0;
+        for (int k = lo; k < hi; ++k) {
+            const int v = snp_variants[k];
+            sum_betas += (double)rowsum[v];
+            if (n_mol) sum_mol += (double)n_mol[v];
+        }
+        for (int k = lo; k < hi; ++k) {
+            const int v = snp_variants[k];
+            double prior = 1.0;
+            if (n_mol) prior = prior + (double)n_mol[v] / (sum_mol + 100.0);
+            prior = prior + (double)rowsum[v] / (sum_betas + 100.0);
+            addition[v] = (float)(prior * default_prior);
+        }
+    }
+}
+
+__global__ void add_prior_kernel(const float* __restrict__ raw, int64_t ld_raw, const float* __restrict__ addition,
+                                 int64_t n_variants, int n_genotypes, float* __restrict__ out, int64_t ld_out) {
+    const int64_t total = n_variants * n_genotypes;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = k / n_genotypes;
+        const int g = (int)(k - v * n_genotypes);
+        out[v * ld_out + g] = __fadd_rn(raw[v * ld_raw + g], addition[v]);
+    }
+}
+
+// Probability table.  Thread (s, g): g runs fastest so a warp reads/writes contiguous pieces of table rows.
+// Work item = (SNP, column) over the padded width ld_table; padded columns are filled with 1.
+__global__ void probs_table_kernel(const float* __restrict__ betas, int64_t ld_betas,
+                                   const float* __restrict__ addition, int64_t ld_add, int n_genotypes,
+                                   const int32_t* __restrict__ snp_offsets, const int32_t* __restrict__ snp_variants,
+                                   int64_t n_snps, float clip_lo, float clip_hi, float* __restrict__ table,
+                                   int64_t ld_table) {
+    const int64_t total = n_snps * ld_table;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = k / ld_table;
+        const int g = (int)(k - s * ld_table);
+        const int lo = snp_offsets[s], hi = snp_offsets[s + 1];
+        if (g >= n_genotypes) {
+            for (int q = lo; q < hi; ++q) table[(int64_t)snp_variants[q] * ld_table + g] = 1.0f;
+            continue;
+        }
+        double den = 0.0;
+        for (int q = lo; q < hi; ++q) {
+            const int64_t v = snp_variants[q];
+            float b = betas[v * ld_betas + g];
+            if (addition) b = __fadd_rn(b, addition[v * ld_add + g]);
+            den += (double)b;
+        }
+        den = fmax(den, 1e-7);
+        for (int q = lo; q < hi; ++q) {
+            const int64_t v = snp_variants[q];
+            float b = betas[v * ld_betas + g];
+            if (addition) b = __fadd_rn(b, addition[v * ld_add + g]);
+            float p = (float)((double)b / den);
+            p = fminf(fmaxf(p, clip_lo), clip_hi);
+            table[v * ld_table + g] = p;
+        }
+    }
+}
+
+static inline int grid_1d(int64_t n, int threads) {
+    int64_t blocks = ceil_div(n > 0 ? n : 1, threads);
+    const int64_t cap = (int64_t)sm_count() * 32;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace dmx
+
+extern "C" {
+
+int dmx_prior_betas(const float* raw_betas, int64_t ld_raw, int64_t n_variants, int32_t n_genotypes,
+                    const int32_t* snp_offsets, const int32_t* snp_variants, int64_t n_snps,
+                    const int64_t* n_mol_per_variant, double default_prior, float* scratch_rowsum,
+                    float* out_betas, int64_t ld_out, void* stream_) {
+    using namespace dmx;
+    if (n_variants <= 0 || n_genotypes <= 0) return 0;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int threads = 256;
+    rowsum_kernel<<<grid_1d(n_variants, threads), threads, 0, stream>>>(raw_betas, ld_raw, n_variants, n_genotypes,
+                                                                       scratch_rowsum);
+    DMX_LAUNCH_CHECK();
+    prior_addition_kernel<<<grid_1d(n_snps, threads), threads, 0, stream>>>(
+        scratch_rowsum, snp_offsets, snp_variants, n_snps, n_mol_per_variant, default_prior, scratch_rowsum);
+    DMX_LAUNCH_CHECK();
+    add_prior_kernel<<<grid_1d(n_variants * n_genotypes, threads), threads, 0, stream>>>(
+        raw_betas, ld_raw, scratch_rowsum, n_variants, n_genotypes, out_betas, ld_out);
+    DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addition, int64_t ld_addition,
+                         int64_t n_variants, int32_t n_genotypes, const int32_t* snp_offsets,
+                         const int32_t* snp_variants, int64_t n_snps, float clip_lo, float clip_hi, float* table,
+                         int64_t ld_table, void* stream_) {
+    using namespace dmx;
+    if (n_variants <= 0 || n_genotypes <= 0) return 0;
+    DMX_REQUIRE(ld_table >= n_genotypes, "ld_table %lld < n_genotypes %d", (long long)ld_table, n_genotypes);
+    const int threads = 256;
+    probs_table_kernel<<<grid_1d(n_snps * ld_table, threads), threads, 0, (cudaStream_t)stream_>>>(
+        betas, ld_betas, addition, ld_addition, n_genotypes, snp_offsets, snp_variants, n_snps, clip_lo, clip_hi,
+        table, ld_table);
+    DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

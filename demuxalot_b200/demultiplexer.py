@@ -1,0 +1,476 @@
+"""
+`Demultiplexer` -- drop-in for demuxalot.Demultiplexer (demuxalot/demux.py:24-392) whose numeric stages
+run as hand-written sm_100a CUDA kernels behind the C ABI of include/demux_b200.h.
+
+Host side (this file) is Python, as the reference is: it flattens the inputs, owns the device buffers
+(torch tensors used purely as memory + streams), calls the kernels through ctypes and assembles the
+DataFrames / genotype objects the reference returns.  No numeric stage has a CPU implementation here; without
+a CUDA device or without libdemux_b200.so every entry point raises.
+
+Stage map (reference lines -> ABI call):
+  pack_calls                     demux.py:302-392  -> dmx_unpack_match_calls, dmx_build_rows, dmx_prior_betas
+  _compute_probs_from_betas      demux.py:267-274  -> dmx_probs_from_betas
+  compute_barcode_logits + softmax  demux.py:246-265,101,152 -> dmx_estep
+  M-step loop                    demux.py:113-118  -> dmx_mstep
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import _native
+from .calls import MOLECULE_DTYPE, SNP_CALL_DTYPE
+
+
+def _require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError('demuxalot_b200 needs a CUDA device (B200 / sm_100a); there is no CPU fallback')
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _to_device(array: np.ndarray, device) -> torch.Tensor:
+    """Host numpy -> device tensor.  Structured arrays travel as their raw packed bytes."""
+    array = np.ascontiguousarray(array)
+    if array.dtype.fields is not None:
+        array = array.view(np.uint8)
+    with warnings.catch_warnings():
+        # read-only inputs (e.g. genotypes.get_betas()) are only ever read through this tensor
+        warnings.filterwarnings('ignore', message='The given NumPy array is not writable')
+        host = torch.from_numpy(array)
+    return host.to(device, non_blocking=True)
+
+
+def n_options(n_genotypes: int, doublet_prior: float) -> int:
+    return n_genotypes if doublet_prior == 0 else n_genotypes * (n_genotypes + 1) // 2
+
+
+def option_names(genotype_names, doublet_prior: float) -> List[str]:
+    """Column names in the order of demux.py:175-191: singlets, then 'Gi+Gj' for i < j, i-major."""
+    names = list(genotype_names)
+    out = list(names)
+    if doublet_prior != 0:
+        assert doublet_prior > 0
+        for i, a in enumerate(names):
+            out.extend(f'{a}+{b}' for b in names[i + 1:])
+    return out
+
+
+@dataclass
+class DevicePack:
+    """Device-resident result of pack_calls: rows in both orders, SNP index, regularised betas."""
+    device: torch.device
+    n_barcodes: int
+    n_variants: int
+    n_genotypes: int
+    n_snps: int
+    n_calls: int
+    n_matched: int
+    n_rows: int
+    barcode_range: Tuple[int, int]
+    # molecule-level calls in original order (variant == -1: unmatched)
+    call_variant: torch.Tensor
+    call_cb: torch.Tensor
+    call_e: torch.Tensor
+    # rows, reference order (variant-major) -- M-step
+    csc_variant: torch.Tensor
+    csc_cb: torch.Tensor
+    csc_e: torch.Tensor
+    csc_count: torch.Tensor
+    variant_offsets: torch.Tensor
+    # rows, barcode-major -- E-step
+    csr_variant: torch.Tensor
+    csr_e: torch.Tensor
+    csr_row: torch.Tensor
+    barcode_offsets: torch.Tensor
+    n_mol: torch.Tensor
+    snp_offsets: torch.Tensor
+    snp_variants: torch.Tensor
+    variant2snp: np.ndarray
+    raw_betas: torch.Tensor
+    betas: torch.Tensor  # regularised betas (demux.py:388), float32 [V, G]
+
+
+class Demultiplexer:
+    """
+    Demultiplexer that can infer (learn) additional information about genotypes to achieve better quality.
+    Same static API and class attributes as the reference (demux.py:24-32).
+    """
+    contribution_power = 2.
+    aggregate_on_snps = False  # the experimental branch (demux.py:204-244) is not part of this path
+    compensation_during_computing_barcode_logits = 0.5
+
+    # B200-specific knobs (not in the reference)
+    estep_flavour = 'fast'  # 'fast' | 'exact', see include/demux_b200.h DMX_ESTEP_*
+    device: Optional[torch.device] = None  # None -> current CUDA device
+    process_group = None  # torch.distributed group for barcode-sharded / multi-lane EM (see distributed.py)
+
+    # ------------------------------------------------------------------------------------------------ helpers
+    @classmethod
+    def _device(cls) -> torch.device:
+        _require_cuda()
+        return torch.device('cuda', torch.cuda.current_device()) if cls.device is None else torch.device(cls.device)
+
+    @classmethod
+    def _flavour(cls) -> int:
+        return {'fast': _native.ESTEP_FAST, 'exact': _native.ESTEP_EXACT}[cls.estep_flavour]
+
+    @staticmethod
+    def _doublet_penalties(n_genotypes: int, doublet_prior: float) -> np.ndarray:
+        """float32 [C] logit offsets (demux.py:158-173); host helper, the kernel applies the same constant."""
+        assert 0 <= doublet_prior < 1
+        out = np.zeros(n_options(n_genotypes, doublet_prior), dtype='float32')
+        if doublet_prior != 0:
+            bonus = np.log(n_genotypes * doublet_prior)
+            bonus -= np.log(n_genotypes * max(n_genotypes - 1, 1) / 2 * (1 - doublet_prior))
+            out[n_genotypes:] = bonus
+        return out
+
+    # ------------------------------------------------------------------------------------------------ pack
+    @classmethod
+    def _pack_device(cls, chromosome2compressed_snp_calls, genotypes, n_barcodes: int, add_data_prior: bool,
+                     barcode_range: Optional[Tuple[int, int]] = None) -> DevicePack:
+        """Device version of pack_calls (demux.py:302-392)."""
+        lib = _native.load()
+        dev = cls._device()
+        index = genotypes.hot_path_index() if hasattr(genotypes, 'hot_path_index') else _foreign_hot_index(genotypes)
+        n_variants, n_genotypes = genotypes.n_variants, genotypes.n_genotypes
+        raw = np.asarray(genotypes.get_betas())
+        assert raw.dtype == np.float32 and raw.shape == (n_variants, n_genotypes)
+        # demux.py:374 -- checked on the host copy (one pass over V x G; the data is about to be uploaded anyway)
+        assert raw.size == 0 or raw.min() >= 0, 'bad genotypes provided, negative betas appeared'
+
+        with torch.cuda.device(dev):
+            stream = _stream()
+            gkeys = _to_device(index['keys_sorted'], dev)
+            gvids = _to_device(index['vids_sorted'], dev)
+            snp_offsets = _to_device(index['snp_offsets'], dev)
+            snp_variants = _to_device(index['snp_variants'], dev)
+
+            chrom2id = index['chrom2id']
+            parts = []
+            for chrom, calls in chromosome2compressed_snp_calls.items():
+                if chrom not in chrom2id:
+                    # demux.py:339-341 skips the chromosome and the counter check at :359 then fails
+                    assert calls.n_snp_calls == 0, \
+                        f'calls on chromosome {chrom!r}, which is absent from the genotypes'
+                    continue
+                if calls.n_snp_calls:
+                    parts.append((chrom2id[chrom], calls))
+            n_calls = sum(c.n_snp_calls for _cid, c in parts)
+            call_variant = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
+            call_cb = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
+            call_e = torch.empty(max(n_calls, 1), dtype=torch.float32, device=dev)
+            done = 0
+            for cid, calls in parts:
+                snp_calls = _as_dtype(calls.snp_calls[:calls.n_snp_calls], SNP_CALL_DTYPE)
+                molecules = _as_dtype(calls.molecules[:calls.n_molecules], MOLECULE_DTYPE)
+                d_calls = _to_device(snp_calls, dev)
+                d_mols = _to_device(molecules, dev)
+                n = calls.n_snp_calls
+                _native.check(lib.dmx_unpack_match_calls(
+                    d_calls.data_ptr(), n, d_mols.data_ptr(), calls.n_molecules, cid,
+                    gkeys.data_ptr(), gvids.data_ptr(), n_variants,
+                    call_variant[done:].data_ptr(), call_cb[done:].data_ptr(), call_e[done:].data_ptr(), stream),
+                    'dmx_unpack_match_calls')
+                done += n
+                # d_calls / d_mols are released when they go out of scope; torch's caching allocator is
+                # stream-ordered, so reuse after the kernel above is safe.
+
+            lo, hi = (0, n_barcodes) if barcode_range is None else barcode_range
+            ws_bytes = lib.dmx_build_rows_workspace_bytes(n_calls, n_variants, n_barcodes)
+            if ws_bytes < 0:
+                _native.check(-1, 'dmx_build_rows_workspace_bytes')
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            cap = max(n_calls, 1)
+            i32 = dict(dtype=torch.int32, device=dev)
+            csc_variant, csc_cb, csc_count = (torch.empty(cap, **i32) for _ in range(3))
+            csr_variant, csr_row = (torch.empty(cap, **i32) for _ in range(2))
+            csc_e = torch.empty(cap, dtype=torch.float32, device=dev)
+            csr_e = torch.empty(cap, dtype=torch.float32, device=dev)
+            variant_offsets = torch.empty(n_variants + 1, dtype=torch.int64, device=dev)
+            barcode_offsets = torch.empty(n_barcodes + 1, dtype=torch.int64, device=dev)
+            n_mol = torch.empty(max(n_variants, 1), dtype=torch.int64, device=dev)
+            h_rows, h_matched = C.c_int64(0), C.c_int64(0)
+            _native.check(lib.dmx_build_rows(
+                call_variant.data_ptr(), call_cb.data_ptr(), call_e.data_ptr(), n_calls, n_variants, n_barcodes,
+                lo, hi, workspace.data_ptr(), ws_bytes,
+                csc_variant.data_ptr(), csc_cb.data_ptr(), csc_e.data_ptr(), csc_count.data_ptr(),
+                variant_offsets.data_ptr(), csr_variant.data_ptr(), csr_e.data_ptr(), csr_row.data_ptr(),
+                barcode_offsets.data_ptr(), n_mol.data_ptr(), C.byref(h_rows), C.byref(h_matched), stream),
+                'dmx_build_rows')
+            del workspace
+            n_rows = int(h_rows.value)
+
+            if add_data_prior and cls.process_group is not None:
+                # multi-lane / sharded EM: the data prior counts molecules of every rank (demux.py:381)
+                import torch.distributed as dist
+                dist.all_reduce(n_mol, op=dist.ReduceOp.SUM, group=cls.process_group)
+
+            raw_dev = _to_device(raw, dev) if raw.size else torch.empty((n_variants, n_genotypes), device=dev)
+            betas = torch.empty((n_variants, n_genotypes), dtype=torch.float32, device=dev)
+            scratch = torch.empty(max(n_variants, 1), dtype=torch.float32, device=dev)
+            _native.check(lib.dmx_prior_betas(
+                raw_dev.data_ptr(), n_genotypes, n_variants, n_genotypes, snp_offsets.data_ptr(),
+                snp_variants.data_ptr(), index['n_snps'], n_mol.data_ptr() if add_data_prior else 0,
+                float(genotypes.default_prior), scratch.data_ptr(), betas.data_ptr(), n_genotypes, stream),
+                'dmx_prior_betas')
+
+        return DevicePack(
+            device=dev, n_barcodes=n_barcodes, n_variants=n_variants, n_genotypes=n_genotypes,
+            n_snps=index['n_snps'], n_calls=n_calls, n_matched=int(h_matched.value), n_rows=n_rows,
+            barcode_range=(lo, hi),
+            call_variant=call_variant[:n_calls], call_cb=call_cb[:n_calls], call_e=call_e[:n_calls],
+            csc_variant=csc_variant[:n_rows], csc_cb=csc_cb[:n_rows], csc_e=csc_e[:n_rows],
+            csc_count=csc_count[:n_rows], variant_offsets=variant_offsets,
+            csr_variant=csr_variant[:n_rows], csr_e=csr_e[:n_rows], csr_row=csr_row[:n_rows],
+            barcode_offsets=barcode_offsets, n_mol=n_mol[:n_variants], snp_offsets=snp_offsets,
+            snp_variants=snp_variants, variant2snp=index['variant2snp'], raw_betas=raw_dev, betas=betas)
+
+    @classmethod
+    def pack_calls(cls, chromosome2compressed_snp_calls, genotypes, add_data_prior: bool, n_barcodes: int = None):
+        """
+        Reference-shaped view of the packed calls (demux.py:302-392): returns
+        (variant_index2snp_index, variant_index2betas, molecule_calls, barcode_calls) as host arrays.
+        `barcode_calls` has the reference's fields except `barcode_snp_count`, which nothing downstream reads.
+        The reference infers nothing about the number of barcodes here; pass `n_barcodes` or it is taken as
+        max(compressed_cb) + 1.
+        """
+        if n_barcodes is None:
+            n_barcodes = 1 + max((int(c.molecules['compressed_cb'][:c.n_molecules].max())
+                                  for c in chromosome2compressed_snp_calls.values() if c.n_molecules), default=0)
+        pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, n_barcodes, add_data_prior)
+        betas = pack.betas.cpu().numpy()
+        betas.flags.writeable = False
+        variant = pack.call_variant.cpu().numpy()
+        keep = variant != -1
+        molecule_calls = np.rec.fromarrays(
+            [variant[keep], pack.variant2snp[variant[keep]], pack.call_cb.cpu().numpy()[keep],
+             pack.call_e.cpu().numpy()[keep]],
+            names=['variant_id', 'snp_id', 'compressed_cb', 'p_base_wrong'])
+        rows_variant = pack.csc_variant.cpu().numpy()
+        barcode_calls = np.rec.fromarrays(
+            [rows_variant, pack.variant2snp[rows_variant], pack.csc_cb.cpu().numpy(), pack.csc_e.cpu().numpy(),
+             pack.csc_count.cpu().numpy().astype(np.int64)],
+            names=['variant_id', 'snp_id', 'compressed_cb', 'p_base_wrong', 'barcode_variant_count'])
+        return pack.variant2snp.copy(), betas, molecule_calls, barcode_calls
+
+    # ------------------------------------------------------------------------------------------------ stages
+    @staticmethod
+    def _table_ld(n_genotypes: int) -> int:
+        return (n_genotypes + 3) // 4 * 4
+
+    @classmethod
+    def _probs_table(cls, pack: DevicePack, addition: Optional[torch.Tensor], p_genotype_clip: float,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(b) of north_star / demux.py:267-274 -> float32 [V, ld] table, ld = G rounded up to 4."""
+        lib = _native.load()
+        ld = cls._table_ld(pack.n_genotypes)
+        if out is None:
+            out = torch.empty((pack.n_variants, ld), dtype=torch.float32, device=pack.device)
+        # probs.clip(p, 1 - p): bounds are Python floats cast to float32 (weak scalars), demux.py:274
+        lo, hi = float(np.float32(p_genotype_clip)), float(np.float32(1 - p_genotype_clip))
+        with torch.cuda.device(pack.device):
+            _native.check(lib.dmx_probs_from_betas(
+                pack.betas.data_ptr(), pack.n_genotypes, _native.ptr(addition), pack.n_genotypes, pack.n_variants,
+                pack.n_genotypes, pack.snp_offsets.data_ptr(), pack.snp_variants.data_ptr(), pack.n_snps, lo, hi,
+                out.data_ptr(), ld, _stream()), 'dmx_probs_from_betas')
+        return out
+
+    @classmethod
+    def _e_step(cls, pack: DevicePack, table: torch.Tensor, doublet_prior: float,
+                prior_logits: Optional[torch.Tensor] = None, want_logits: bool = True, want_post: bool = True,
+                want_singlets: bool = False, buffers: Optional[dict] = None):
+        """(c) of north_star / demux.py:246-265 + softmax.  Returns (logits, posteriors, singlet_posteriors)."""
+        lib = _native.load()
+        dev = pack.device
+        n_cols = n_options(pack.n_genotypes, doublet_prior)
+        buffers = {} if buffers is None else buffers
+
+        def buf(name, shape):
+            t = buffers.get(name)
+            if t is None or tuple(t.shape) != tuple(shape):
+                t = torch.empty(shape, dtype=torch.float32, device=dev)
+                buffers[name] = t
+            return t
+
+        logits = buf('logits', (pack.n_barcodes, n_cols)) if want_logits else None
+        post = buf('post', (pack.n_barcodes, n_cols)) if want_post else None
+        singlets = buf('singlets', (pack.n_barcodes, pack.n_genotypes)) if want_singlets else None
+        workspace, ws_bytes = None, 0
+        if logits is None:
+            ws_bytes = lib.dmx_estep_workspace_bytes(pack.n_barcodes, pack.n_genotypes, float(doublet_prior))
+            workspace = buffers.get('estep_ws')
+            if workspace is None or workspace.numel() < ws_bytes:
+                workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                buffers['estep_ws'] = workspace
+        with torch.cuda.device(dev):
+            _native.check(lib.dmx_estep(
+                pack.barcode_offsets.data_ptr(), pack.csr_variant.data_ptr(), pack.csr_e.data_ptr(),
+                pack.n_barcodes, table.data_ptr(), table.shape[1], pack.n_genotypes, float(doublet_prior),
+                _native.ptr(prior_logits), n_cols,
+                _native.ptr(logits), n_cols, _native.ptr(post), n_cols, _native.ptr(singlets), pack.n_genotypes,
+                _native.ptr(workspace), ws_bytes, cls._flavour(), _stream()), 'dmx_estep')
+        return logits, post, singlets
+
+    @classmethod
+    def _m_step(cls, pack: DevicePack, singlets: torch.Tensor, out: Optional[torch.Tensor] = None,
+                out64: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(d) of north_star / demux.py:113-118 -> genotype_addition float32 [V, G] (+ all-reduce when sharded)."""
+        lib = _native.load()
+        dev = pack.device
+        sharded = cls.process_group is not None
+        if out is None:
+            out = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float32, device=dev)
+        if sharded and out64 is None:
+            out64 = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.dmx_mstep(
+                pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
+                singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, float(cls.contribution_power),
+                0 if sharded else out.data_ptr(), pack.n_genotypes, _native.ptr(out64), pack.n_genotypes,
+                0, pack.n_variants, _stream()), 'dmx_mstep')
+            if sharded:
+                # (f) of north_star: one all-reduce of the partial variant x genotype sums per EM iteration.
+                # Partials travel as float64 so the single rounding to float32 happens after the global sum,
+                # exactly as on one GPU.
+                import torch.distributed as dist
+                dist.all_reduce(out64, op=dist.ReduceOp.SUM, group=cls.process_group)
+                _native.check(lib.dmx_round_f64_to_f32(
+                    out64.data_ptr(), pack.n_genotypes, out.data_ptr(), pack.n_genotypes, pack.n_variants,
+                    pack.n_genotypes, _stream()), 'dmx_round_f64_to_f32')
+        return out
+
+    # ------------------------------------------------------------------------------------------------ public API
+    @classmethod
+    def predict_posteriors(cls, chromosome2compressed_snp_calls, genotypes, barcode_handler,
+                           p_genotype_clip=0.01, doublet_prior=0.35):
+        """One E-step with the given genotypes (demux.py:120-156): returns (logits_df, probs_df)."""
+        assert not cls.aggregate_on_snps, 'aggregate_on_snps=True is not implemented on the CUDA path'
+        pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
+                                add_data_prior=False)
+        table = cls._probs_table(pack, None, p_genotype_clip)
+        assert bool(torch.isfinite(table).all())  # demux.py:135
+        logits, post, _ = cls._e_step(pack, table, doublet_prior)
+        logits_np, post_np = logits.cpu().numpy(), post.cpu().numpy()
+        names = option_names(genotypes.genotype_names, doublet_prior)
+        index = list(barcode_handler.ordered_barcodes)
+        logits_df = pd.DataFrame(data=logits_np, index=index, columns=names)
+        logits_df.index.name = 'BARCODE'
+        probs_df = pd.DataFrame(data=post_np, index=index, columns=names)
+        probs_df.index.name = 'BARCODE'
+        return logits_df, probs_df
+
+    @classmethod
+    def _prior_logits_to_device(cls, barcode_prior_logits, n_barcodes: int, n_cols: int, dev):
+        if barcode_prior_logits is None:
+            return None
+        assert barcode_prior_logits.shape == (n_barcodes, n_cols), 'wrong shape of priors'
+        return _to_device(np.asarray(barcode_prior_logits, dtype=np.float32), dev)
+
+    @classmethod
+    def staged_genotype_learning(cls, chromosome2compressed_snp_calls, genotypes, barcode_handler,
+                                 n_iterations=5, p_genotype_clip=0.01, doublet_prior=0.,
+                                 barcode_prior_logits: np.ndarray = None):
+        """
+        Generator over EM iterations (demux.py:68-118); yields (posterior DataFrame, debug dict with
+        'barcode_logits', 'genotype_prior', 'genotype_addition') exactly like the reference, which means a
+        device->host copy of the [B, C] matrices per iteration.  `learn_genotypes` avoids those copies.
+        """
+        assert 0 <= doublet_prior < 1
+        assert not cls.aggregate_on_snps, 'aggregate_on_snps=True is not implemented on the CUDA path'
+        n_cols = n_options(genotypes.n_genotypes, doublet_prior)
+        if barcode_prior_logits is not None:
+            assert barcode_prior_logits.shape == (barcode_handler.n_barcodes, n_cols), 'wrong shape of priors'
+        pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
+                                add_data_prior=True)
+        prior_dev = cls._prior_logits_to_device(barcode_prior_logits, barcode_handler.n_barcodes, n_cols, pack.device)
+        names = option_names(genotypes.genotype_names, doublet_prior)
+        betas_host = pack.betas.cpu().numpy()
+        betas_host.flags.writeable = False
+        addition = torch.zeros_like(pack.betas)
+        for iteration in range(n_iterations):
+            table = cls._probs_table(pack, addition, p_genotype_clip)
+            logits, post, singlets = cls._e_step(
+                pack, table, doublet_prior, prior_logits=prior_dev if iteration == 0 else None, want_singlets=True)
+            post_df = pd.DataFrame(data=post.cpu().numpy(), index=barcode_handler.ordered_barcodes, columns=names)
+            debug_information = {
+                'barcode_logits': logits.cpu().numpy(),
+                'genotype_prior': betas_host,
+                'genotype_addition': addition.cpu().numpy(),
+            }
+            yield post_df, debug_information
+            addition = cls._m_step(pack, singlets)
+
+    @classmethod
+    def learn_genotypes(cls, chromosome2compressed_snp_calls, genotypes, barcode_handler, n_iterations=5,
+                        p_genotype_clip=0.01, doublet_prior=0., barcode_prior_logits: np.ndarray = None):
+        """
+        EM refinement of the genotypes (demux.py:34-66): returns (learnt genotypes, last posteriors).
+        Same results as exhausting `staged_genotype_learning`, but everything stays on the device between
+        iterations, only the singlet posteriors are materialised for the M-step, and the M-step after the last
+        E-step (whose result the reference discards, demux.py:55,113) is not run.
+        """
+        assert 0 <= doublet_prior < 1
+        assert not cls.aggregate_on_snps, 'aggregate_on_snps=True is not implemented on the CUDA path'
+        assert n_iterations >= 1, 'the reference unpacks the last generator item: n_iterations must be >= 1'
+        n_cols = n_options(genotypes.n_genotypes, doublet_prior)
+        if barcode_prior_logits is not None:
+            assert barcode_prior_logits.shape == (barcode_handler.n_barcodes, n_cols), 'wrong shape of priors'
+        pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
+                                add_data_prior=True)
+        prior_dev = cls._prior_logits_to_device(barcode_prior_logits, barcode_handler.n_barcodes, n_cols, pack.device)
+        post, addition = cls._em_iterations(pack, n_iterations, p_genotype_clip, doublet_prior, prior_dev)
+        names = option_names(genotypes.genotype_names, doublet_prior)
+        post_df = pd.DataFrame(data=post.cpu().numpy(), index=barcode_handler.ordered_barcodes, columns=names)
+        learnt_betas = (pack.raw_betas + addition).cpu().numpy()  # float32 add, demux.py:65
+        return genotypes._with_betas(learnt_betas), post_df
+
+    @classmethod
+    def _em_iterations(cls, pack: DevicePack, n_iterations: int, p_genotype_clip: float, doublet_prior: float,
+                       prior_logits: Optional[torch.Tensor]):
+        """Device-resident EM loop; returns (posteriors [B, C] of the last E-step, addition that fed it)."""
+        buffers: dict = {}
+        addition = torch.zeros_like(pack.betas)
+        spare = torch.empty_like(pack.betas)
+        spare64 = torch.empty(pack.betas.shape, dtype=torch.float64, device=pack.device) \
+            if cls.process_group is not None else None
+        table = None
+        post = None
+        for iteration in range(n_iterations):
+            last = iteration == n_iterations - 1
+            table = cls._probs_table(pack, addition, p_genotype_clip, out=table)
+            _, post, singlets = cls._e_step(
+                pack, table, doublet_prior, prior_logits=prior_logits if iteration == 0 else None,
+                want_logits=False, want_post=last, want_singlets=not last, buffers=buffers)
+            if not last:
+                new_addition = cls._m_step(pack, singlets, out=spare, out64=spare64)
+                spare, addition = addition, new_addition
+        return post, addition
+
+
+def _as_dtype(array: np.ndarray, dtype: np.dtype) -> np.ndarray:
+    """Structured input with the expected packed layout passes through untouched; anything else is converted."""
+    if array.dtype == dtype:
+        return array
+    out = np.empty(len(array), dtype=dtype)
+    for name in dtype.names:
+        out[name] = array[name]
+    return out
+
+
+def _foreign_hot_index(genotypes) -> dict:
+    """hot_path_index() for a reference `ProbabilisticGenotypes` object (duck typing on var2varid)."""
+    from .genotype_store import ProbabilisticGenotypes
+    shim = ProbabilisticGenotypes.__new__(ProbabilisticGenotypes)
+    shim.var2varid = genotypes.var2varid
+    index = shim.hot_path_index()
+    return index

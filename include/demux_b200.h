@@ -1,0 +1,138 @@
+/*
+ * libdemux_b200 -- C ABI of the B200-native likelihood / EM core for demuxalot.
+ *
+ * The reference (arogozhnikov/demuxalot v0.4.3) is pure Python and has no FFI seam; its boundary for
+ * this path is `demuxalot.Demultiplexer` (demuxalot/demux.py:24-392).  Each entry point below replaces
+ * one numpy stage of that class and cites it.  The Python host (`demuxalot_b200/demultiplexer.py`) binds
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every data pointer is a DEVICE pointer into caller-owned memory
+ *    unless the parameter name starts with `h_` (host);
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on that stream unless stated;
+ *  - return value: 0 = OK, negative = error; text via dmx_last_error() (thread-local);
+ *  - nothing throws across the ABI; the library keeps no global state, scratch memory is passed in
+ *    by the caller (`*_workspace_bytes` queries), so calls on distinct streams/devices are independent;
+ *  - table / posterior matrices are row-major float32 with an explicit leading dimension (`ld*`, in
+ *    elements).
+ */
+#ifndef DEMUX_B200_H
+#define DEMUX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMX_ABI_VERSION 1
+
+/* E-step arithmetic flavours (see DESIGN.md "E-step") */
+#define DMX_ESTEP_EXACT 0 /* per-term float32 argument roundings + logf of demux.py:261, float64 accumulation */
+#define DMX_ESTEP_FAST 1  /* a = fma(P, 1-e, e'), products of 8 row factors, one lg2 per product, float64 accumulation */
+
+/* ---- boundary smoke ------------------------------------------------------------------------------- */
+int dmx_abi_version(void);
+const char* dmx_last_error(void);
+/* fills sm_count, cc_major, cc_minor, l2_bytes, total_mem_bytes for `device` */
+int dmx_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int64_t* l2_bytes,
+                    int64_t* total_mem_bytes);
+
+/* ---- (a2) variant matching: demux.py:334-358 --------------------------------------------------------
+ * Unpacks one chromosome's packed records (snp_counter.py:88-98: snp_calls 13 B, molecules 12 B),
+ * builds key = chrom_id << 40 | pos << 8 | base and binary-searches it in the sorted genotype keys.
+ * Writes, for call k, out_variant[k] (variant id or -1), out_cb[k] (molecules[mol].compressed_cb) and
+ * out_e[k] (p_base_wrong, bit pattern preserved).
+ */
+int dmx_unpack_match_calls(const uint8_t* snp_calls_packed, int64_t n_calls,
+                           const uint8_t* molecules_packed, int64_t n_molecules,
+                           int64_t chrom_id,
+                           const int64_t* geno_keys_sorted, const int32_t* geno_vids_sorted, int64_t n_variants,
+                           int32_t* out_variant, int32_t* out_cb, float* out_e, void* stream);
+
+/* ---- (a3) group + UMI-combine: demux.py:276-300, 362-363, 381 ---------------------------------------
+ * Input: molecule-level calls (variant or -1, barcode, p_base_wrong) in original call order.
+ * Output (capacity n_calls each, the first *h_n_rows entries are valid):
+ *   rows in the reference's order, ascending (variant_id, compressed_cb)  ["CSC", used by the M-step]:
+ *     csc_variant, csc_cb, csc_e (= ordered float32 product, no flush-to-zero), csc_count (group size),
+ *     variant_offsets int64 [n_variants + 1]
+ *   the same rows stably re-sorted by barcode                              ["CSR", used by the E-step]:
+ *     csr_variant, csr_e, csr_row (index of the row in CSC order), barcode_offsets int64 [n_barcodes + 1]
+ *   n_mol_per_variant int64 [n_variants] = matched molecule-level calls per variant (demux.py:381)
+ * Only calls whose barcode lies in [barcode_lo, barcode_hi) become rows (barcode sharding across GPUs; pass
+ * 0, n_barcodes for everything); n_mol_per_variant always counts every matched call.
+ * Synchronises `stream` once to return *h_n_rows and *h_n_matched on the host.
+ */
+int64_t dmx_build_rows_workspace_bytes(int64_t n_calls, int64_t n_variants, int64_t n_barcodes);
+int dmx_build_rows(const int32_t* call_variant, const int32_t* call_cb, const float* call_e, int64_t n_calls,
+                   int64_t n_variants, int64_t n_barcodes, int64_t barcode_lo, int64_t barcode_hi,
+                   void* workspace, int64_t workspace_bytes,
+                   int32_t* csc_variant, int32_t* csc_cb, float* csc_e, int32_t* csc_count,
+                   int64_t* variant_offsets,
+                   int32_t* csr_variant, float* csr_e, int32_t* csr_row, int64_t* barcode_offsets,
+                   int64_t* n_mol_per_variant,
+                   int64_t* h_n_rows, int64_t* h_n_matched, void* stream);
+
+/* ---- (a4) regularised betas: demux.py:367-390 --------------------------------------------------------
+ * out[v, g] = raw[v, g] + float32((1 + [n_mol] n_mol[v] / (sum_snp n_mol + 100)
+ *                                   + rowsum(raw)[v] / (sum_snp rowsum + 100)) * default_prior)
+ * rowsum is numpy's float32 pairwise sum; the rest is float64.  n_mol_per_variant may be NULL
+ * (predict_posteriors).  snp_offsets/snp_variants: CSR SNP -> variants, ascending variant id.
+ * scratch: float32 [n_variants].
+ */
+int dmx_prior_betas(const float* raw_betas, int64_t ld_raw, int64_t n_variants, int32_t n_genotypes,
+                    const int32_t* snp_offsets, const int32_t* snp_variants, int64_t n_snps,
+                    const int64_t* n_mol_per_variant, double default_prior,
+                    float* scratch_rowsum, float* out_betas, int64_t ld_out, void* stream);
+
+/* ---- (a6) probability table: demux.py:267-274 --------------------------------------------------------
+ * b = betas (+ addition, float32 add, demux.py:90);  den[s, g] = float64 sum over the SNP's variants;
+ * P[v, g] = clip(float32(double(b) / max(den, 1e-7)), clip_lo, clip_hi); columns g in [G, ld_table) = 1.
+ */
+int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addition, int64_t ld_addition,
+                         int64_t n_variants, int32_t n_genotypes,
+                         const int32_t* snp_offsets, const int32_t* snp_variants, int64_t n_snps,
+                         float clip_lo, float clip_hi, float* table, int64_t ld_table, void* stream);
+
+/* ---- (a7-a10) E-step: demux.py:246-265, 158-191, 97-101 ----------------------------------------------
+ * logits[b, c] = float32(pen[c] + sum_{rows r of b} log(p_c[v_r] (1 - e_r) + max(e_r, 1e-4))), columns:
+ * G singlets then (doublet_prior != 0) the G(G-1)/2 pairs i < j, i-major.  Optional prior_logits [B, C]
+ * (float32) is added after the sum (demux.py:97-99).  Then a row softmax (float32).
+ * Outputs (each may be NULL): logits [B, ld_logits], posteriors [B, ld_post], singlet posteriors
+ * [B, ld_singlet] (first G columns of the softmax; the only part the M-step reads, demux.py:115).
+ * `table` is the output of dmx_probs_from_betas with ld_table a multiple of 4.
+ * scratch: float32 [n_barcodes * C] when `logits` is NULL (workspace query below), else unused.
+ */
+int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior);
+int dmx_estep(const int64_t* barcode_offsets, const int32_t* csr_variant, const float* csr_e,
+              int64_t n_barcodes, const float* table, int64_t ld_table, int32_t n_genotypes,
+              double doublet_prior, const float* prior_logits, int64_t ld_prior,
+              float* logits, int64_t ld_logits, float* posteriors, int64_t ld_post,
+              float* singlet_posteriors, int64_t ld_singlet,
+              void* workspace, int64_t workspace_bytes, int32_t flavour, void* stream);
+
+/* row softmax only (scipy.special.softmax(x, axis=-1), demux.py:101,152); outputs as in dmx_estep */
+int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int32_t n_cols,
+                     float* posteriors, int64_t ld_post, float* singlet_posteriors, int64_t ld_singlet,
+                     int32_t n_singlets, void* stream);
+
+/* ---- (a11) M-step: demux.py:113-118 -------------------------------------------------------------------
+ * addition[v, g] = float32(sum_{rows r of v, ascending} (post[cb_r, g] (1 - e_r)) ^ power), g < G,
+ * float32 terms accumulated in float64.  Variants in [variant_lo, variant_hi) are processed so the caller
+ * can tile the variant range and overlap the all-reduce of finished tiles.  When `addition64` is not
+ * NULL the unrounded float64 sums are stored there as well (multi-GPU partials).
+ */
+int dmx_mstep(const int64_t* variant_offsets, const int32_t* csc_cb, const float* csc_e,
+              const float* singlet_posteriors, int64_t ld_singlet, int32_t n_genotypes, double power,
+              float* addition, int64_t ld_addition, double* addition64, int64_t ld_addition64,
+              int64_t variant_lo, int64_t variant_hi, void* stream);
+
+/* float32(out) = float32(in64) elementwise over a [rows, cols] matrix (after an all-reduce of float64 partials) */
+int dmx_round_f64_to_f32(const double* in64, int64_t ld_in, float* out, int64_t ld_out, int64_t n_rows,
+                         int32_t n_cols, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEMUX_B200_H */

