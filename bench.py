@@ -163,6 +163,17 @@ def time_oracle_slice(ds, n_b: int, n_jobs: int, repeats: int = 1):
     return times, len(rows['variant_id']), logits.shape[1]
 
 
+def calibrate_slice(ds, n_jobs: int, budget_s: float) -> int:
+    """Number of leading barcodes whose oracle predict_posteriors call takes about budget_s (two-point fit)."""
+    n1, n2 = 8, 48
+    (t1,), _, _ = time_oracle_slice(ds, n1, n_jobs)
+    (t2,), _, _ = time_oracle_slice(ds, n2, n_jobs)
+    slope = max(t2 - t1, 1e-4) / (n2 - n1)
+    fixed = max(t1 - n1 * slope, 0.0)
+    n_b = int((budget_s - fixed) / slope) if budget_s > fixed else n2
+    return max(n2, min(ds.barcode_handler.n_barcodes, n_b))
+
+
 # ------------------------------------------------------------------------------------------------- CPU arm
 def run_reference(args, rank: int):
     if rank != 0:
@@ -170,14 +181,9 @@ def run_reference(args, rank: int):
     from demuxalot_b200.synthetic import make_config
     import oracle
     cores = oracle.demux_oracle.default_n_jobs()
-    budget_s = 150.0
-    probe_b = 24
+    budget_s = 150.0  # whole run, so that the default invocation ends within a few minutes
     ds = make_config(args.workload, scale=args.scale, n_barcodes=4096 if args.scale == 1.0 else 64)
-    (t_probe,), rows_probe, n_cols = time_oracle_slice(ds, probe_b, cores)
-    fixed = min(t_probe, 3.0)  # dict flattening etc. does not scale with the slice
-    per_barcode = max(t_probe - fixed, 1e-3) / probe_b
-    n_b = int(max(probe_b, min(ds.barcode_handler.n_barcodes,
-                               (budget_s / (args.steps + args.warmup) - fixed) / per_barcode)))
+    n_b = calibrate_slice(ds, cores, budget_s / (args.steps + args.warmup))
     times, rows, n_cols = time_oracle_slice(ds, n_b, cores, repeats=args.warmup + args.steps)
     timed = times[args.warmup:]
     ms = 1e3 * sum(timed) / len(timed)
@@ -368,10 +374,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     }
 
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        probe_b = 16
-        (t_probe,), _, _ = time_oracle_slice(ds, probe_b, 1)
-        fixed = min(t_probe, 3.0)
-        n_b = int(max(probe_b, min(B, (15.0 - fixed) / (max(t_probe - fixed, 1e-3) / probe_b))))
+        n_b = calibrate_slice(ds, 1, 15.0)
         (t_cpu,), rows_cpu, _ = time_oracle_slice(ds, n_b, 1)
         line['cpu_baseline'] = {
             'value': rows_cpu * C / t_cpu, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'seconds': t_cpu,
