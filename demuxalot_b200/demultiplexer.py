@@ -112,6 +112,7 @@ class Demultiplexer:
     estep_flavour = 'fast'  # 'fast' | 'exact', see include/demux_b200.h DMX_ESTEP_*
     device: Optional[torch.device] = None  # None -> current CUDA device
     process_group = None  # torch.distributed group for barcode-sharded / multi-lane EM (see distributed.py)
+    mstep_allreduce_tiles = 4  # variant-range tiles: all-reduce of tile k overlaps the M-step of tile k + 1
 
     # ------------------------------------------------------------------------------------------------ helpers
     @classmethod
@@ -283,6 +284,7 @@ class Demultiplexer:
                 pack.betas.data_ptr(), pack.n_genotypes, _native.ptr(addition), pack.n_genotypes, pack.n_variants,
                 pack.n_genotypes, pack.snp_offsets.data_ptr(), pack.snp_variants.data_ptr(), pack.n_snps, lo, hi,
                 out.data_ptr(), ld, _stream()), 'dmx_probs_from_betas')
+        out.dmx_floor = lo  # every entry is >= the clip: lets the E-step pick its product length
         return out
 
     @classmethod
@@ -318,7 +320,8 @@ class Demultiplexer:
                 pack.n_barcodes, table.data_ptr(), table.shape[1], pack.n_genotypes, float(doublet_prior),
                 _native.ptr(prior_logits), n_cols,
                 _native.ptr(logits), n_cols, _native.ptr(post), n_cols, _native.ptr(singlets), pack.n_genotypes,
-                _native.ptr(workspace), ws_bytes, cls._flavour(), _stream()), 'dmx_estep')
+                _native.ptr(workspace), ws_bytes, cls._flavour(), float(getattr(table, 'dmx_floor', 0.0)),
+                _stream()), 'dmx_estep')
         return logits, post, singlets
 
     @classmethod
@@ -333,20 +336,34 @@ class Demultiplexer:
         if sharded and out64 is None:
             out64 = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
-            _native.check(lib.dmx_mstep(
-                pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
-                singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, float(cls.contribution_power),
-                0 if sharded else out.data_ptr(), pack.n_genotypes, _native.ptr(out64), pack.n_genotypes,
-                0, pack.n_variants, _stream()), 'dmx_mstep')
-            if sharded:
-                # (f) of north_star: one all-reduce of the partial variant x genotype sums per EM iteration.
-                # Partials travel as float64 so the single rounding to float32 happens after the global sum,
-                # exactly as on one GPU.
-                import torch.distributed as dist
-                dist.all_reduce(out64, op=dist.ReduceOp.SUM, group=cls.process_group)
-                _native.check(lib.dmx_round_f64_to_f32(
-                    out64.data_ptr(), pack.n_genotypes, out.data_ptr(), pack.n_genotypes, pack.n_variants,
-                    pack.n_genotypes, _stream()), 'dmx_round_f64_to_f32')
+            def launch(v_lo: int, v_hi: int) -> None:
+                _native.check(lib.dmx_mstep(
+                    pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
+                    singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, float(cls.contribution_power),
+                    0 if sharded else out.data_ptr(), pack.n_genotypes, _native.ptr(out64), pack.n_genotypes,
+                    v_lo, v_hi, _stream()), 'dmx_mstep')
+
+            if not sharded:
+                launch(0, pack.n_variants)
+                return out
+            # (f) of north_star: the partial variant x genotype sums of all barcode shards are combined with one
+            # sum all-reduce per EM iteration.  The variant range is cut into tiles: NCCL reduces tile k (on its
+            # own stream, async_op) while the M-step kernel computes tile k + 1.  Partials travel as float64 so
+            # the single rounding to float32 happens after the global sum, exactly as on one GPU.
+            import torch.distributed as dist
+            n_tiles = max(1, min(cls.mstep_allreduce_tiles, pack.n_variants))
+            bounds = [pack.n_variants * k // n_tiles for k in range(n_tiles + 1)]
+            pending = []
+            for v_lo, v_hi in zip(bounds[:-1], bounds[1:]):
+                if v_hi > v_lo:
+                    launch(v_lo, v_hi)
+                    pending.append(dist.all_reduce(out64[v_lo:v_hi], op=dist.ReduceOp.SUM,
+                                                   group=cls.process_group, async_op=True))
+            for work in pending:
+                work.wait()
+            _native.check(lib.dmx_round_f64_to_f32(
+                out64.data_ptr(), pack.n_genotypes, out.data_ptr(), pack.n_genotypes, pack.n_variants,
+                pack.n_genotypes, _stream()), 'dmx_round_f64_to_f32')
         return out
 
     # ------------------------------------------------------------------------------------------------ public API

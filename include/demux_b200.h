@@ -103,6 +103,8 @@ int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addi
  * [B, ld_singlet] (first G columns of the softmax; the only part the M-step reads, demux.py:115).
  * `table` is the output of dmx_probs_from_betas with ld_table a multiple of 4.
  * scratch: float32 [n_barcodes * C] when `logits` is NULL (workspace query below), else unused.
+ * `table_floor`: a lower bound of the table entries (the clip_lo given to dmx_probs_from_betas), or 0 if
+ * unknown; the FAST flavour uses it to decide how many row factors it may multiply before taking one log.
  */
 int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior);
 int dmx_estep(const int64_t* barcode_offsets, const int32_t* csr_variant, const float* csr_e,
@@ -110,7 +112,7 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* csr_variant, const 
               double doublet_prior, const float* prior_logits, int64_t ld_prior,
               float* logits, int64_t ld_logits, float* posteriors, int64_t ld_post,
               float* singlet_posteriors, int64_t ld_singlet,
-              void* workspace, int64_t workspace_bytes, int32_t flavour, void* stream);
+              void* workspace, int64_t workspace_bytes, int32_t flavour, float table_floor, void* stream);
 
 /* row softmax only (scipy.special.softmax(x, axis=-1), demux.py:101,152); outputs as in dmx_estep */
 int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int32_t n_cols,
