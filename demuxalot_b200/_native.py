@@ -28,7 +28,9 @@ SIGNATURES = {
     'dmx_probs_from_betas': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _f32, _f32, _ptr,
                                        _i64, _ptr]),
     'dmx_estep_workspace_bytes': (_i64, [_i64, _i32, _f64]),
-    'dmx_estep': (C.c_int, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
+    'dmx_barcode_schedule_workspace_bytes': (_i64, [_i64]),
+    'dmx_barcode_schedule': (C.c_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr]),
+    'dmx_estep': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                             _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr]),
     'dmx_softmax_rows': (C.c_int, [_ptr, _i64, _i64, _i32, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     'dmx_mstep': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),

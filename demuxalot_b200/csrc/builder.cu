@@ -171,6 +171,16 @@ __global__ void gather_csr_kernel(const uint32_t* __restrict__ perm, const int32
     }
 }
 
+// longest-processing-time-first schedule: barcodes by descending row count (ties: ascending id, the sort is stable)
+__global__ void schedule_keys_kernel(const int64_t* __restrict__ offsets, int64_t n_barcodes,
+                                     uint32_t* __restrict__ keys, uint32_t* __restrict__ ids) {
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < n_barcodes; b += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rows = offsets[b + 1] - offsets[b];
+        keys[b] = 0xFFFFFFFFu - (uint32_t)(rows < 0xFFFFFFFFll ? rows : 0xFFFFFFFFll);
+        ids[b] = (uint32_t)b;
+    }
+}
+
 static int bits_for(int64_t max_value) {  // bits needed to represent values 0..max_value
     int b = 1;
     while ((max_value >> b) != 0) ++b;
@@ -227,6 +237,35 @@ int dmx_unpack_match_calls(const uint8_t* snp_calls_packed, int64_t n_calls, con
         snp_calls_packed, n_calls, molecules_packed, n_molecules, chrom_id, geno_keys_sorted, geno_vids_sorted,
         n_variants, out_variant, out_cb, out_e);
     DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+int64_t dmx_barcode_schedule_workspace_bytes(int64_t n_barcodes) {
+    size_t temp = 0;
+    const int64_t m = n_barcodes > 0 ? n_barcodes : 1;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                        (const uint32_t*)nullptr, (uint32_t*)nullptr, m) != cudaSuccess)
+        return -1;
+    return dmx::round_up((int64_t)temp, 256) + 3 * dmx::round_up(4 * m, 256);
+}
+
+int dmx_barcode_schedule(const int64_t* barcode_offsets, int64_t n_barcodes, int32_t* order, void* workspace,
+                         int64_t workspace_bytes, void* stream_) {
+    using namespace dmx;
+    if (n_barcodes <= 0) return 0;
+    DMX_REQUIRE(workspace_bytes >= dmx_barcode_schedule_workspace_bytes(n_barcodes), "schedule workspace too small");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t slice = round_up(4 * n_barcodes, 256);
+    uint8_t* ws = (uint8_t*)workspace;
+    uint32_t* keys_in = (uint32_t*)ws;
+    uint32_t* keys_out = (uint32_t*)(ws + slice);
+    uint32_t* ids_in = (uint32_t*)(ws + 2 * slice);
+    void* temp = ws + 3 * slice;
+    size_t temp_bytes = (size_t)(workspace_bytes - 3 * slice);
+    schedule_keys_kernel<<<grid_for(n_barcodes, 256), 256, 0, stream>>>(barcode_offsets, n_barcodes, keys_in, ids_in);
+    DMX_LAUNCH_CHECK();
+    DMX_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, (const uint32_t*)keys_in, keys_out,
+                                             (const uint32_t*)ids_in, (uint32_t*)order, n_barcodes, 0, 32, stream));
     return 0;
 }
 

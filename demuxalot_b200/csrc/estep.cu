@@ -30,7 +30,7 @@ constexpr int FLUSH_ROWS = 8;  // row factors multiplied before one lg2 (singlet
 constexpr float ERROR_FLOOR = 1e-4f;
 
 // estep_pairs.cu
-int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* csr_variant, const float* csr_e,
+int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant, const float* csr_e,
                        int64_t n_barcodes, const float* table, int64_t ld_table, int G, double doublet_prior,
                        float table_floor, const float* prior_logits, int64_t ld_prior, float* logits,
                        int64_t ld_logits, int flavour, cudaStream_t stream);
@@ -41,6 +41,7 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* csr_varian
 
 template <int FLAVOUR, int SLOTS>
 __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __restrict__ offsets,
+                                                             const int32_t* __restrict__ order,
                                                              const int32_t* __restrict__ variant,
                                                              const float* __restrict__ e_arr,
                                                              const float* __restrict__ table, int64_t ld_table,
@@ -50,40 +51,61 @@ __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __re
     __shared__ double partial[4][SLOTS * 32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int64_t barcode = blockIdx.x;
+    const int64_t barcode = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;
     const int64_t lo = offsets[barcode], hi = offsets[barcode + 1];
 
     double acc[SLOTS];
-    float prod[SLOTS];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { acc[s] = 0.0; prod[s] = 1.f; }
+    for (int s = 0; s < SLOTS; ++s) acc[s] = 0.0;
 
-    int in_prod = 0;
-    for (int64_t r = lo + warp; r < hi; r += 4) {
-        const int64_t v = variant[r];
-        const float e = e_arr[r];
-        const float w = __fsub_rn(1.f, e);
-        const float ef = fmaxf(e, ERROR_FLOOR);
-        const float* row = table + v * ld_table;
+    // a warp takes every 4th batch of 32 rows: one coalesced load of the row records, then the rows are walked
+    // with shuffles, eight table-row gathers (4G bytes each, coalesced over the lanes) in flight at a time
+    for (int64_t base = lo + 32 * warp; base < hi; base += 32 * 4) {
+        const int n = (int)(hi - base < 32 ? hi - base : 32);
+        const int32_t my_v = lane < n ? __ldg(variant + base + lane) : 0;
+        const float my_e = lane < n ? __ldg(e_arr + base + lane) : 0.f;
+        for (int k = 0; k < n; k += FLUSH_ROWS) {
+            float pg[FLUSH_ROWS][SLOTS], w[FLUSH_ROWS], ef[FLUSH_ROWS];
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int g = lane + 32 * s;
-            const float pg = (g < n_genotypes) ? __ldg(row + g) : 1.f;
-            if (FLAVOUR == DMX_ESTEP_FAST) {
-                prod[s] *= fmaf(pg, w, ef);
-            } else {
-                acc[s] += (double)logf(__fadd_rn(__fmul_rn(pg, w), ef));
+            for (int u = 0; u < FLUSH_ROWS; ++u) {
+                const int src = k + u < n ? k + u : k;  // clamp; masked out below
+                const int32_t v = __shfl_sync(0xffffffffu, my_v, src);
+                const float e = __shfl_sync(0xffffffffu, my_e, src);
+                w[u] = __fsub_rn(1.f, e);
+                ef[u] = fmaxf(e, ERROR_FLOOR);
+                const float* row = table + (int64_t)v * ld_table;
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) {
+                    const int g = lane + 32 * s;
+                    pg[u][s] = (g < n_genotypes) ? __ldg(row + g) : 1.f;
+                }
             }
-        }
-        if (FLAVOUR == DMX_ESTEP_FAST && ++in_prod == FLUSH_ROWS) {
+            if (FLAVOUR == DMX_ESTEP_FAST) {
+                float prod[SLOTS];
 #pragma unroll
-            for (int s = 0; s < SLOTS; ++s) { acc[s] += (double)__log2f(prod[s]); prod[s] = 1.f; }
-            in_prod = 0;
+                for (int s = 0; s < SLOTS; ++s) prod[s] = 1.f;
+#pragma unroll
+                for (int u = 0; u < FLUSH_ROWS; ++u)
+                    if (k + u < n) {
+#pragma unroll
+                        for (int s = 0; s < SLOTS; ++s) prod[s] *= fmaf(pg[u][s], w[u], ef[u]);
+                    }
+#pragma unroll
+                for (int s = 0; s < SLOTS; ++s) acc[s] += (double)__log2f(prod[s]);
+            } else {
+#pragma unroll
+                for (int u = 0; u < FLUSH_ROWS; ++u)
+                    if (k + u < n) {
+#pragma unroll
+                        for (int s = 0; s < SLOTS; ++s)
+                            acc[s] += (double)logf(__fadd_rn(__fmul_rn(pg[u][s], w[u]), ef[u]));
+                    }
+            }
         }
     }
     if (FLAVOUR == DMX_ESTEP_FAST) {
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) acc[s] = (acc[s] + (double)__log2f(prod[s])) * 0.693147180559945309417232;
+        for (int s = 0; s < SLOTS; ++s) acc[s] *= 0.693147180559945309417232;
     }
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) partial[warp][s * 32 + lane] = acc[s];
@@ -149,11 +171,11 @@ static int launch_softmax(const float* logits, int64_t ld_logits, int64_t n_rows
 
 template <int FLAVOUR>
 static int launch_singlets(int slots, unsigned grid, cudaStream_t stream, const int64_t* offsets,
-                           const int32_t* variant, const float* e, const float* table, int64_t ld_table, int G,
+                           const int32_t* order, const int32_t* variant, const float* e, const float* table, int64_t ld_table, int G,
                            const float* prior, int64_t ld_prior, float* logits, int64_t ld_logits) {
 #define DMX_SINGLETS_CASE(S)                                                                                       \
     case S:                                                                                                        \
-        estep_singlets_kernel<FLAVOUR, S><<<grid, 128, 0, stream>>>(offsets, variant, e, table, ld_table, G, prior, \
+        estep_singlets_kernel<FLAVOUR, S><<<grid, 128, 0, stream>>>(offsets, order, variant, e, table, ld_table, G, prior, \
                                                                     ld_prior, logits, ld_logits);                 \
         break;
     switch (slots) {
@@ -187,7 +209,8 @@ int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int
                                n_singlets, (cudaStream_t)stream);
 }
 
-int dmx_estep(const int64_t* barcode_offsets, const int32_t* csr_variant, const float* csr_e, int64_t n_barcodes,
+int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant,
+              const float* csr_e, int64_t n_barcodes,
               const float* table, int64_t ld_table, int32_t n_genotypes, double doublet_prior,
               const float* prior_logits, int64_t ld_prior, float* logits, int64_t ld_logits, float* posteriors,
               int64_t ld_post, float* singlet_posteriors, int64_t ld_singlet, void* workspace,
@@ -219,14 +242,14 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* csr_variant, const 
         while (slots < slots_needed) slots *= 2;
         int rc;
         if (flavour == DMX_ESTEP_FAST)
-            rc = launch_singlets<DMX_ESTEP_FAST>(slots, (unsigned)n_barcodes, stream, barcode_offsets, csr_variant,
+            rc = launch_singlets<DMX_ESTEP_FAST>(slots, (unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
                                                  csr_e, table, ld_table, G, prior_logits, ld_prior, out_logits, ld_out);
         else
-            rc = launch_singlets<DMX_ESTEP_EXACT>(slots, (unsigned)n_barcodes, stream, barcode_offsets, csr_variant,
+            rc = launch_singlets<DMX_ESTEP_EXACT>(slots, (unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
                                                   csr_e, table, ld_table, G, prior_logits, ld_prior, out_logits, ld_out);
         if (rc) return rc;
     } else {
-        const int rc = launch_estep_pairs(barcode_offsets, csr_variant, csr_e, n_barcodes, table, ld_table, G,
+        const int rc = launch_estep_pairs(barcode_offsets, barcode_order, csr_variant, csr_e, n_barcodes, table, ld_table, G,
                                           doublet_prior, table_floor, prior_logits, ld_prior, out_logits, ld_out,
                                           flavour, stream);
         if (rc) return rc;

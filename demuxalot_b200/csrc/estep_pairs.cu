@@ -31,6 +31,7 @@ constexpr float ERROR_FLOOR = 1e-4f;
 
 struct PairsParams {
     const int64_t* offsets;
+    const int32_t* order;  // launch schedule (barcodes by descending row count) or nullptr
     const int32_t* variant;
     const float* e;
     const float* table;
@@ -80,8 +81,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int n_threads = blockDim.x;
-    const int64_t barcode = blockIdx.x / p.ctas_per_barcode;
-    const int cta_in_barcode = (int)(blockIdx.x - barcode * p.ctas_per_barcode);
+    const int64_t slot_in_grid = blockIdx.x / p.ctas_per_barcode;
+    const int cta_in_barcode = (int)(blockIdx.x - slot_in_grid * p.ctas_per_barcode);
+    const int64_t barcode = p.order ? (int64_t)p.order[slot_in_grid] : slot_in_grid;
 
     const int tile_local = tid % p.tiles_per_cta;
     const int rg = tid / p.tiles_per_cta;
@@ -369,12 +371,13 @@ static int launch_variant(const PairsParams& p, unsigned grid, int threads, size
 // table_floor: lower bound of the table entries (the clip of demux.py:274), 0 if unknown.  It decides how many
 // row factors (>= 2 (table_floor + 1e-4) each) can be multiplied in float32 without leaving the normal range.
 // Tuning overrides (experiments only): DMX_RG, DMX_FLUSHES, DMX_FLUSH_ROWS, DMX_MAX_THREADS, DMX_VERBOSE.
-int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* csr_variant, const float* csr_e,
+int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant, const float* csr_e,
                        int64_t n_barcodes, const float* table, int64_t ld_table, int G, double doublet_prior,
                        float table_floor, const float* prior_logits, int64_t ld_prior, float* logits,
                        int64_t ld_logits, int flavour, cudaStream_t stream) {
     PairsParams p;
     p.offsets = barcode_offsets;
+    p.order = barcode_order;
     p.variant = csr_variant;
     p.e = csr_e;
     p.table = table;
@@ -393,31 +396,20 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* csr_varian
     int flush_rows = (long_products_safe && env_int("DMX_FLUSH_ROWS", 16) == 16) ? 16 : 8;
 
     // Shape of a CTA: `ctas_per_barcode` CTAs split the tiles of a barcode, each with `row_groups` copies of its
-    // tile slice, at most 256 threads (two CTAs resident per SM).  Pick the split that keeps the most lanes
-    // busy, discounted by the share of staging work per row (every CTA stages whole table rows).
+    // tile slice, at most 256 threads (two CTAs resident per SM).
     // measured on B200 (scripts/sweep_estep.py): 128-thread CTAs win while one CTA covers a barcode's tiles
     // (G = 32: 1.58 vs 1.71 ms), 256-thread CTAs win once the tiles are split over CTAs (G = 200: 7.9 vs 11.2 ms)
     int max_threads = env_int("DMX_MAX_THREADS", n_tiles <= 64 ? 128 : MAX_THREADS);
     if (max_threads > MAX_THREADS || max_threads < 32) max_threads = MAX_THREADS;
     {
-        double best_score = -1.0;
-        p.ctas_per_barcode = 1; p.tiles_per_cta = n_tiles; p.row_groups = 1;
+        // as few CTAs per barcode as the thread budget allows (every CTA stages whole table rows, so splitting
+        // a barcode's tiles repeats the staging), then as many row groups as fit
+        p.ctas_per_barcode = (int)ceil_div(n_tiles, max_threads);
+        p.tiles_per_cta = (int)ceil_div(n_tiles, p.ctas_per_barcode);
+        int rg = max_threads / p.tiles_per_cta;
         const int forced_rg = env_int("DMX_RG", 0);
-        for (int ctas = 1; ctas <= n_tiles; ++ctas) {
-            const int tpc = (int)ceil_div(n_tiles, ctas);
-            if (tpc > max_threads) continue;
-            for (int rg = 1; rg <= 16 && tpc * rg <= max_threads; ++rg) {
-                if (forced_rg > 0 && rg != forced_rg && tpc * forced_rg <= max_threads) continue;
-                const int thr = (int)round_up(tpc * rg, 32);
-                const double busy = (double)n_tiles * rg / ((double)ctas * thr);
-                const double staging_share = quads * 8.0 / (tpc * 20.0);
-                const double score = busy / (1.0 + staging_share);
-                if (score > best_score + 1e-9) {
-                    best_score = score; p.ctas_per_barcode = ctas; p.tiles_per_cta = tpc; p.row_groups = rg;
-                }
-            }
-            if (tpc <= 8) break;
-        }
+        if (forced_rg > 0 && forced_rg * p.tiles_per_cta <= MAX_THREADS) rg = forced_rg;
+        p.row_groups = rg < 1 ? 1 : (rg > 16 ? 16 : rg);
     }
     const int compute_threads = p.tiles_per_cta * p.row_groups;
     DMX_REQUIRE(compute_threads <= MAX_THREADS, "internal: CTA too large");

@@ -49,6 +49,17 @@ def _to_device(array: np.ndarray, device) -> torch.Tensor:
     return host.to(device, non_blocking=True)
 
 
+def _to_host(*tensors: torch.Tensor):
+    """Device -> host through pinned staging buffers (torch caches them), one synchronisation for all."""
+    staged = []
+    for t in tensors:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        staged.append(h)
+    torch.cuda.current_stream().synchronize()
+    return [h.numpy() for h in staged]
+
+
 def n_options(n_genotypes: int, doublet_prior: float) -> int:
     return n_genotypes if doublet_prior == 0 else n_genotypes * (n_genotypes + 1) // 2
 
@@ -91,6 +102,7 @@ class DevicePack:
     csr_e: torch.Tensor
     csr_row: torch.Tensor
     barcode_offsets: torch.Tensor
+    barcode_order: torch.Tensor  # launch schedule: barcodes by descending row count
     n_mol: torch.Tensor
     snp_offsets: torch.Tensor
     snp_variants: torch.Tensor
@@ -112,6 +124,7 @@ class Demultiplexer:
     estep_flavour = 'fast'  # 'fast' | 'exact', see include/demux_b200.h DMX_ESTEP_*
     device: Optional[torch.device] = None  # None -> current CUDA device
     process_group = None  # torch.distributed group for barcode-sharded / multi-lane EM (see distributed.py)
+    schedule_barcodes = True  # launch the deepest barcodes first (dmx_barcode_schedule)
     mstep_allreduce_tiles = 4  # variant-range tiles: all-reduce of tile k overlaps the M-step of tile k + 1
 
     # ------------------------------------------------------------------------------------------------ helpers
@@ -146,8 +159,6 @@ class Demultiplexer:
         n_variants, n_genotypes = genotypes.n_variants, genotypes.n_genotypes
         raw = np.asarray(genotypes.get_betas())
         assert raw.dtype == np.float32 and raw.shape == (n_variants, n_genotypes)
-        # demux.py:374 -- checked on the host copy (one pass over V x G; the data is about to be uploaded anyway)
-        assert raw.size == 0 or raw.min() >= 0, 'bad genotypes provided, negative betas appeared'
 
         with torch.cuda.device(dev):
             stream = _stream()
@@ -186,6 +197,9 @@ class Demultiplexer:
                 # d_calls / d_mols are released when they go out of scope; torch's caching allocator is
                 # stream-ordered, so reuse after the kernel above is safe.
 
+            raw_dev = _to_device(raw, dev) if raw.size else torch.empty((n_variants, n_genotypes), device=dev)
+            betas_min = raw_dev.min() if raw.size else None
+
             lo, hi = (0, n_barcodes) if barcode_range is None else barcode_range
             ws_bytes = lib.dmx_build_rows_workspace_bytes(n_calls, n_variants, n_barcodes)
             if ws_bytes < 0:
@@ -210,13 +224,19 @@ class Demultiplexer:
                 'dmx_build_rows')
             del workspace
             n_rows = int(h_rows.value)
+            barcode_order = torch.empty(max(n_barcodes, 1), dtype=torch.int32, device=dev)
+            sched_bytes = lib.dmx_barcode_schedule_workspace_bytes(n_barcodes)
+            sched_ws = torch.empty(max(sched_bytes, 1), dtype=torch.uint8, device=dev)
+            _native.check(lib.dmx_barcode_schedule(barcode_offsets.data_ptr(), n_barcodes, barcode_order.data_ptr(),
+                                                   sched_ws.data_ptr(), sched_bytes, stream), 'dmx_barcode_schedule')
 
             if add_data_prior and cls.process_group is not None:
                 # multi-lane / sharded EM: the data prior counts molecules of every rank (demux.py:381)
                 import torch.distributed as dist
                 dist.all_reduce(n_mol, op=dist.ReduceOp.SUM, group=cls.process_group)
 
-            raw_dev = _to_device(raw, dev) if raw.size else torch.empty((n_variants, n_genotypes), device=dev)
+            if betas_min is not None:  # demux.py:374; the value is ready, dmx_build_rows synchronised the stream
+                assert float(betas_min) >= 0, 'bad genotypes provided, negative betas appeared'
             betas = torch.empty((n_variants, n_genotypes), dtype=torch.float32, device=dev)
             scratch = torch.empty(max(n_variants, 1), dtype=torch.float32, device=dev)
             _native.check(lib.dmx_prior_betas(
@@ -233,7 +253,7 @@ class Demultiplexer:
             csc_variant=csc_variant[:n_rows], csc_cb=csc_cb[:n_rows], csc_e=csc_e[:n_rows],
             csc_count=csc_count[:n_rows], variant_offsets=variant_offsets,
             csr_variant=csr_variant[:n_rows], csr_e=csr_e[:n_rows], csr_row=csr_row[:n_rows],
-            barcode_offsets=barcode_offsets, n_mol=n_mol[:n_variants], snp_offsets=snp_offsets,
+            barcode_offsets=barcode_offsets, barcode_order=barcode_order[:n_barcodes], n_mol=n_mol[:n_variants], snp_offsets=snp_offsets,
             snp_variants=snp_variants, variant2snp=index['variant2snp'], raw_betas=raw_dev, betas=betas)
 
     @classmethod
@@ -316,8 +336,8 @@ class Demultiplexer:
                 buffers['estep_ws'] = workspace
         with torch.cuda.device(dev):
             _native.check(lib.dmx_estep(
-                pack.barcode_offsets.data_ptr(), pack.csr_variant.data_ptr(), pack.csr_e.data_ptr(),
-                pack.n_barcodes, table.data_ptr(), table.shape[1], pack.n_genotypes, float(doublet_prior),
+                pack.barcode_offsets.data_ptr(), pack.barcode_order.data_ptr() if cls.schedule_barcodes else 0,
+                pack.csr_variant.data_ptr(), pack.csr_e.data_ptr(), pack.n_barcodes, table.data_ptr(), table.shape[1], pack.n_genotypes, float(doublet_prior),
                 _native.ptr(prior_logits), n_cols,
                 _native.ptr(logits), n_cols, _native.ptr(post), n_cols, _native.ptr(singlets), pack.n_genotypes,
                 _native.ptr(workspace), ws_bytes, cls._flavour(), float(getattr(table, 'dmx_floor', 0.0)),
@@ -375,15 +395,15 @@ class Demultiplexer:
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
                                 add_data_prior=False)
         table = cls._probs_table(pack, None, p_genotype_clip)
-        assert bool(torch.isfinite(table).all())  # demux.py:135
+        table_is_finite = torch.isfinite(table).all()  # demux.py:135; read back together with the results
         logits, post, _ = cls._e_step(pack, table, doublet_prior)
-        logits_np, post_np = logits.cpu().numpy(), post.cpu().numpy()
-        names = option_names(genotypes.genotype_names, doublet_prior)
-        index = list(barcode_handler.ordered_barcodes)
-        logits_df = pd.DataFrame(data=logits_np, index=index, columns=names)
-        logits_df.index.name = 'BARCODE'
-        probs_df = pd.DataFrame(data=post_np, index=index, columns=names)
-        probs_df.index.name = 'BARCODE'
+        logits_np, post_np, finite = _to_host(logits, post, table_is_finite)
+        assert bool(finite), 'non-finite genotype probabilities'
+        names = pd.Index(option_names(genotypes.genotype_names, doublet_prior))
+        index = pd.Index(list(barcode_handler.ordered_barcodes), name='BARCODE')
+        # copy=False: the arrays were just created by the download and are owned by nothing else
+        logits_df = pd.DataFrame(data=logits_np, index=index, columns=names, copy=False)
+        probs_df = pd.DataFrame(data=post_np, index=index, columns=names, copy=False)
         return logits_df, probs_df
 
     @classmethod
@@ -418,11 +438,12 @@ class Demultiplexer:
             table = cls._probs_table(pack, addition, p_genotype_clip)
             logits, post, singlets = cls._e_step(
                 pack, table, doublet_prior, prior_logits=prior_dev if iteration == 0 else None, want_singlets=True)
-            post_df = pd.DataFrame(data=post.cpu().numpy(), index=barcode_handler.ordered_barcodes, columns=names)
+            post_np, logits_np, addition_np = _to_host(post, logits, addition)
+            post_df = pd.DataFrame(data=post_np, index=barcode_handler.ordered_barcodes, columns=names, copy=False)
             debug_information = {
-                'barcode_logits': logits.cpu().numpy(),
+                'barcode_logits': logits_np,
                 'genotype_prior': betas_host,
-                'genotype_addition': addition.cpu().numpy(),
+                'genotype_addition': addition_np,
             }
             yield post_df, debug_information
             addition = cls._m_step(pack, singlets)
@@ -447,8 +468,8 @@ class Demultiplexer:
         prior_dev = cls._prior_logits_to_device(barcode_prior_logits, barcode_handler.n_barcodes, n_cols, pack.device)
         post, addition = cls._em_iterations(pack, n_iterations, p_genotype_clip, doublet_prior, prior_dev)
         names = option_names(genotypes.genotype_names, doublet_prior)
-        post_df = pd.DataFrame(data=post.cpu().numpy(), index=barcode_handler.ordered_barcodes, columns=names)
-        learnt_betas = (pack.raw_betas + addition).cpu().numpy()  # float32 add, demux.py:65
+        post_np, learnt_betas = _to_host(post, pack.raw_betas + addition)  # float32 add, demux.py:65
+        post_df = pd.DataFrame(data=post_np, index=barcode_handler.ordered_barcodes, columns=names, copy=False)
         return genotypes._with_betas(learnt_betas), post_df
 
     @classmethod

@@ -74,6 +74,13 @@ int dmx_build_rows(const int32_t* call_variant, const int32_t* call_cb, const fl
                    int64_t* n_mol_per_variant,
                    int64_t* h_n_rows, int64_t* h_n_matched, void* stream);
 
+/* Launch schedule for the barcode-parallel E-step: order[k] = k-th barcode by descending row count, so the
+ * deepest barcodes start first and the tail of the grid is made of short ones (no reference counterpart; the
+ * results do not depend on it). */
+int64_t dmx_barcode_schedule_workspace_bytes(int64_t n_barcodes);
+int dmx_barcode_schedule(const int64_t* barcode_offsets, int64_t n_barcodes, int32_t* order, void* workspace,
+                         int64_t workspace_bytes, void* stream);
+
 /* ---- (a4) regularised betas: demux.py:367-390 --------------------------------------------------------
  * out[v, g] = raw[v, g] + float32((1 + [n_mol] n_mol[v] / (sum_snp n_mol + 100)
  *                                   + rowsum(raw)[v] / (sum_snp rowsum + 100)) * default_prior)
@@ -107,8 +114,9 @@ int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addi
  * unknown; the FAST flavour uses it to decide how many row factors it may multiply before taking one log.
  */
 int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior);
-int dmx_estep(const int64_t* barcode_offsets, const int32_t* csr_variant, const float* csr_e,
-              int64_t n_barcodes, const float* table, int64_t ld_table, int32_t n_genotypes,
+int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order /* dmx_barcode_schedule, or NULL */,
+              const int32_t* csr_variant, const float* csr_e, int64_t n_barcodes,
+              const float* table, int64_t ld_table, int32_t n_genotypes,
               double doublet_prior, const float* prior_logits, int64_t ld_prior,
               float* logits, int64_t ld_logits, float* posteriors, int64_t ld_post,
               float* singlet_posteriors, int64_t ld_singlet,
