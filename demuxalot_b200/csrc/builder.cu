@@ -80,7 +80,7 @@ __global__ void make_keys_kernel(const int32_t* __restrict__ variant, const int3
             uint64_t key = sentinel;
             if (v >= 0 && (int64_t)v < n_variants) {
                 if (b >= 0 && (int64_t)b < n_barcodes) {
-                    atomicAdd(&n_mol[v], 1ull);  // the data prior counts every matched call (demux.py:381)
+                    if (n_mol) atomicAdd(&n_mol[v], 1ull);  // the data prior counts every matched call (demux.py:381)
                     if ((int64_t)b >= barcode_lo && (int64_t)b < barcode_hi) {  // this shard's barcodes
                         matched = true;
                         key = ((uint64_t)v << cb_bits) | (uint64_t)b;
@@ -307,7 +307,8 @@ int dmx_build_rows(const int32_t* call_variant, const int32_t* call_cb, const fl
 
     const int threads = 256;
     DMX_CUDA(cudaMemsetAsync(counters, 0, sizeof(BuildCounters), stream));
-    if (n_variants > 0) DMX_CUDA(cudaMemsetAsync(n_mol_per_variant, 0, sizeof(int64_t) * n_variants, stream));
+    if (n_variants > 0 && n_mol_per_variant)
+        DMX_CUDA(cudaMemsetAsync(n_mol_per_variant, 0, sizeof(int64_t) * n_variants, stream));
 
     int64_t n_rows = 0, n_matched = 0;
     if (n_calls > 0) {

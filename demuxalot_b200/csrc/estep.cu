@@ -39,7 +39,10 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
 // singlets only (doublet_prior == 0): one CTA of 4 warps per barcode, lanes over genotypes
 // ---------------------------------------------------------------------------------------------------------------
 
-template <int FLAVOUR, int SLOTS>
+// Each lane owns 4 consecutive genotypes (one 128-bit load of a table row), a row needs LPR lanes, a warp works on
+// 32 / LPR rows at once with eight rows in flight; row records of 32 rows are read with one coalesced load per
+// array and handed around with shuffles.
+template <int FLAVOUR, int LPR, int SLOTS>
 __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __restrict__ offsets,
                                                              const int32_t* __restrict__ order,
                                                              const int32_t* __restrict__ variant,
@@ -48,80 +51,101 @@ __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __re
                                                              int n_genotypes, const float* __restrict__ prior,
                                                              int64_t ld_prior, float* __restrict__ logits,
                                                              int64_t ld_logits) {
-    __shared__ double partial[4][SLOTS * 32];
+    constexpr int RGW = 32 / LPR;                  // rows a warp processes at once
+    constexpr int WAVES = 8 / RGW > 0 ? 8 / RGW : 1;
+    constexpr int PASSES_PER_FLUSH = FLUSH_ROWS / WAVES > 0 ? FLUSH_ROWS / WAVES : 1;
+    __shared__ double partial[4][SLOTS * 4][32];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    const int sub = lane % LPR, rgw = lane / LPR;
+    const int n_quads = (int)(ld_table / 4);
     const int64_t barcode = order ? (int64_t)order[blockIdx.x] : (int64_t)blockIdx.x;
     const int64_t lo = offsets[barcode], hi = offsets[barcode + 1];
 
-    double acc[SLOTS];
+    double acc[SLOTS][4];
+    float prod[SLOTS][4];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) acc[s] = 0.0;
+    for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { acc[s][c] = 0.0; prod[s][c] = 1.f; }
 
-    // a warp takes every 4th batch of 32 rows: one coalesced load of the row records, then the rows are walked
-    // with shuffles, eight table-row gathers (4G bytes each, coalesced over the lanes) in flight at a time
+    auto flush = [&]() {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[s][c] += (double)__log2f(prod[s][c]); prod[s][c] = 1.f; }
+    };
+
     for (int64_t base = lo + 32 * warp; base < hi; base += 32 * 4) {
         const int n = (int)(hi - base < 32 ? hi - base : 32);
         const int32_t my_v = lane < n ? __ldg(variant + base + lane) : 0;
         const float my_e = lane < n ? __ldg(e_arr + base + lane) : 0.f;
-        for (int k = 0; k < n; k += FLUSH_ROWS) {
-            float pg[FLUSH_ROWS][SLOTS], w[FLUSH_ROWS], ef[FLUSH_ROWS];
+        int pass = 0;
+        for (int k0 = 0; k0 < n; k0 += RGW * WAVES, ++pass) {
+            float4 pg[WAVES][SLOTS];
+            float w[WAVES], ef[WAVES];
+            bool valid[WAVES];
 #pragma unroll
-            for (int u = 0; u < FLUSH_ROWS; ++u) {
-                const int src = k + u < n ? k + u : k;  // clamp; masked out below
+            for (int u = 0; u < WAVES; ++u) {
+                const int k = k0 + u * RGW + rgw;
+                const int src = k < n ? k : 0;
+                valid[u] = k < n;
                 const int32_t v = __shfl_sync(0xffffffffu, my_v, src);
                 const float e = __shfl_sync(0xffffffffu, my_e, src);
                 w[u] = __fsub_rn(1.f, e);
                 ef[u] = fmaxf(e, ERROR_FLOOR);
-                const float* row = table + (int64_t)v * ld_table;
+                const float4* row = reinterpret_cast<const float4*>(table + (int64_t)v * ld_table);
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
-                    const int g = lane + 32 * s;
-                    pg[u][s] = (g < n_genotypes) ? __ldg(row + g) : 1.f;
+                    const int q = sub + LPR * s;
+                    pg[u][s] = (q < n_quads && valid[u]) ? __ldg(row + q) : make_float4(1.f, 1.f, 1.f, 1.f);
                 }
             }
-            if (FLAVOUR == DMX_ESTEP_FAST) {
-                float prod[SLOTS];
 #pragma unroll
-                for (int s = 0; s < SLOTS; ++s) prod[s] = 1.f;
+            for (int u = 0; u < WAVES; ++u)
 #pragma unroll
-                for (int u = 0; u < FLUSH_ROWS; ++u)
-                    if (k + u < n) {
+                for (int s = 0; s < SLOTS; ++s) {
+                    const float p4[4] = {pg[u][s].x, pg[u][s].y, pg[u][s].z, pg[u][s].w};
 #pragma unroll
-                        for (int s = 0; s < SLOTS; ++s) prod[s] *= fmaf(pg[u][s], w[u], ef[u]);
+                    for (int c = 0; c < 4; ++c) {
+                        if (FLAVOUR == DMX_ESTEP_FAST) {
+                            prod[s][c] *= valid[u] ? fmaf(p4[c], w[u], ef[u]) : 1.f;
+                        } else {
+                            const float t = logf(__fadd_rn(__fmul_rn(p4[c], w[u]), ef[u]));
+                            acc[s][c] += (double)(valid[u] ? t : 0.f);
+                        }
                     }
-#pragma unroll
-                for (int s = 0; s < SLOTS; ++s) acc[s] += (double)__log2f(prod[s]);
-            } else {
-#pragma unroll
-                for (int u = 0; u < FLUSH_ROWS; ++u)
-                    if (k + u < n) {
-#pragma unroll
-                        for (int s = 0; s < SLOTS; ++s)
-                            acc[s] += (double)logf(__fadd_rn(__fmul_rn(pg[u][s], w[u]), ef[u]));
-                    }
-            }
+                }
+            if (FLAVOUR == DMX_ESTEP_FAST && (pass + 1) % PASSES_PER_FLUSH == 0) flush();
         }
+        if (FLAVOUR == DMX_ESTEP_FAST) flush();
     }
-    if (FLAVOUR == DMX_ESTEP_FAST) {
+    // combine the row groups of the warp in a fixed order, then the four warps
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) acc[s] *= 0.693147180559945309417232;
-    }
+    for (int s = 0; s < SLOTS; ++s)
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) partial[warp][s * 32 + lane] = acc[s];
+        for (int c = 0; c < 4; ++c) {
+            double total = acc[s][c];
+#pragma unroll
+            for (int g = 1; g < RGW; ++g) total += __shfl_sync(0xffffffffu, acc[s][c], (sub + g * LPR) & 31);
+            if (FLAVOUR == DMX_ESTEP_FAST) total *= 0.693147180559945309417232;
+            partial[warp][s * 4 + c][lane] = total;
+        }
     __syncthreads();
-    if (warp == 0) {
+    if (warp == 0 && rgw == 0) {
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int g = lane + 32 * s;
-            if (g < n_genotypes) {
-                const double sum = ((partial[0][s * 32 + lane] + partial[1][s * 32 + lane]) +
-                                    partial[2][s * 32 + lane]) + partial[3][s * 32 + lane];
-                float logit = (float)(0.0 + sum);
-                if (prior) logit = (float)((double)logit + (double)prior[barcode * ld_prior + g]);
-                logits[barcode * ld_logits + g] = logit;
+        for (int s = 0; s < SLOTS; ++s)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int g = 4 * (sub + LPR * s) + c;
+                if (g < n_genotypes) {
+                    const double sum = ((partial[0][s * 4 + c][lane] + partial[1][s * 4 + c][lane]) +
+                                        partial[2][s * 4 + c][lane]) + partial[3][s * 4 + c][lane];
+                    float logit = (float)(0.0 + sum);
+                    if (prior) logit = (float)((double)logit + (double)prior[barcode * ld_prior + g]);
+                    logits[barcode * ld_logits + g] = logit;
+                }
             }
-        }
     }
 }
 
@@ -170,25 +194,23 @@ static int launch_softmax(const float* logits, int64_t ld_logits, int64_t n_rows
 }
 
 template <int FLAVOUR>
-static int launch_singlets(int slots, unsigned grid, cudaStream_t stream, const int64_t* offsets,
-                           const int32_t* order, const int32_t* variant, const float* e, const float* table, int64_t ld_table, int G,
+static int launch_singlets(unsigned grid, cudaStream_t stream, const int64_t* offsets, const int32_t* order,
+                           const int32_t* variant, const float* e, const float* table, int64_t ld_table, int G,
                            const float* prior, int64_t ld_prior, float* logits, int64_t ld_logits) {
-#define DMX_SINGLETS_CASE(S)                                                                                       \
-    case S:                                                                                                        \
-        estep_singlets_kernel<FLAVOUR, S><<<grid, 128, 0, stream>>>(offsets, order, variant, e, table, ld_table, G, prior, \
-                                                                    ld_prior, logits, ld_logits);                 \
-        break;
-    switch (slots) {
-        DMX_SINGLETS_CASE(1)
-        DMX_SINGLETS_CASE(2)
-        DMX_SINGLETS_CASE(4)
-        DMX_SINGLETS_CASE(8)
-        DMX_SINGLETS_CASE(16)
-        default:
-            set_error("singlet E-step supports up to 512 genotypes");
-            return -2;
+    const int quads = (int)(ld_table / 4);
+#define DMX_SINGLETS(LPR, SLOTS)                                                                                  \
+    estep_singlets_kernel<FLAVOUR, LPR, SLOTS><<<grid, 128, 0, stream>>>(offsets, order, variant, e, table, ld_table, \
+                                                                         G, prior, ld_prior, logits, ld_logits)
+    if (quads <= 8) DMX_SINGLETS(8, 1);
+    else if (quads <= 16) DMX_SINGLETS(16, 1);
+    else if (quads <= 32) DMX_SINGLETS(32, 1);
+    else if (quads <= 64) DMX_SINGLETS(32, 2);
+    else if (quads <= 128) DMX_SINGLETS(32, 4);
+    else {
+        set_error("singlet E-step supports up to 512 genotypes");
+        return -2;
     }
-#undef DMX_SINGLETS_CASE
+#undef DMX_SINGLETS
     DMX_LAUNCH_CHECK();
     return 0;
 }
@@ -237,15 +259,12 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
     }
 
     if (doublet_prior == 0) {
-        const int slots_needed = (int)ceil_div(G, 32);
-        int slots = 1;
-        while (slots < slots_needed) slots *= 2;
         int rc;
         if (flavour == DMX_ESTEP_FAST)
-            rc = launch_singlets<DMX_ESTEP_FAST>(slots, (unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
+            rc = launch_singlets<DMX_ESTEP_FAST>((unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
                                                  csr_e, table, ld_table, G, prior_logits, ld_prior, out_logits, ld_out);
         else
-            rc = launch_singlets<DMX_ESTEP_EXACT>(slots, (unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
+            rc = launch_singlets<DMX_ESTEP_EXACT>((unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
                                                   csr_e, table, ld_table, G, prior_logits, ld_prior, out_logits, ld_out);
         if (rc) return rc;
     } else {

@@ -76,6 +76,9 @@ __device__ __forceinline__ float lg2_raw(float x) {
     return y;
 }
 
+// Variants measured and dropped (scripts/sweep_estep.py, profiles/): 8x4 tiles (168 registers, same speed),
+// __launch_bounds__(256, 3) (80 registers, spills, 15-30 % slower), an integer float->double widening to take
+// F2F off the XU pipe (no gain), scalar FADD/FMUL instead of the packed forms (8-10 % slower).
 template <int FLAVOUR, int FLUSH_ROWS>
 __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const PairsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];

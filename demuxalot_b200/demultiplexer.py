@@ -213,14 +213,15 @@ class Demultiplexer:
             csr_e = torch.empty(cap, dtype=torch.float32, device=dev)
             variant_offsets = torch.empty(n_variants + 1, dtype=torch.int64, device=dev)
             barcode_offsets = torch.empty(n_barcodes + 1, dtype=torch.int64, device=dev)
-            n_mol = torch.empty(max(n_variants, 1), dtype=torch.int64, device=dev)
+            n_mol = torch.zeros(max(n_variants, 1), dtype=torch.int64, device=dev)  # filled only for the data prior
             h_rows, h_matched = C.c_int64(0), C.c_int64(0)
             _native.check(lib.dmx_build_rows(
                 call_variant.data_ptr(), call_cb.data_ptr(), call_e.data_ptr(), n_calls, n_variants, n_barcodes,
                 lo, hi, workspace.data_ptr(), ws_bytes,
                 csc_variant.data_ptr(), csc_cb.data_ptr(), csc_e.data_ptr(), csc_count.data_ptr(),
                 variant_offsets.data_ptr(), csr_variant.data_ptr(), csr_e.data_ptr(), csr_row.data_ptr(),
-                barcode_offsets.data_ptr(), n_mol.data_ptr(), C.byref(h_rows), C.byref(h_matched), stream),
+                barcode_offsets.data_ptr(), n_mol.data_ptr() if add_data_prior else 0, C.byref(h_rows),
+                C.byref(h_matched), stream),
                 'dmx_build_rows')
             del workspace
             n_rows = int(h_rows.value)
@@ -326,7 +327,12 @@ class Demultiplexer:
 
         logits = buf('logits', (pack.n_barcodes, n_cols)) if want_logits else None
         post = buf('post', (pack.n_barcodes, n_cols)) if want_post else None
-        singlets = buf('singlets', (pack.n_barcodes, pack.n_genotypes)) if want_singlets else None
+        singlets = None
+        if want_singlets:  # leading dimension padded to 4 (128-bit loads in the M-step); padding stays zero
+            shape = (pack.n_barcodes, cls._table_ld(pack.n_genotypes))
+            singlets = buffers.get('singlets')
+            if singlets is None or tuple(singlets.shape) != shape:
+                singlets = buffers['singlets'] = torch.zeros(shape, dtype=torch.float32, device=dev)
         workspace, ws_bytes = None, 0
         if logits is None:
             ws_bytes = lib.dmx_estep_workspace_bytes(pack.n_barcodes, pack.n_genotypes, float(doublet_prior))
@@ -339,7 +345,8 @@ class Demultiplexer:
                 pack.barcode_offsets.data_ptr(), pack.barcode_order.data_ptr() if cls.schedule_barcodes else 0,
                 pack.csr_variant.data_ptr(), pack.csr_e.data_ptr(), pack.n_barcodes, table.data_ptr(), table.shape[1], pack.n_genotypes, float(doublet_prior),
                 _native.ptr(prior_logits), n_cols,
-                _native.ptr(logits), n_cols, _native.ptr(post), n_cols, _native.ptr(singlets), pack.n_genotypes,
+                _native.ptr(logits), n_cols, _native.ptr(post), n_cols, _native.ptr(singlets),
+                cls._table_ld(pack.n_genotypes),
                 _native.ptr(workspace), ws_bytes, cls._flavour(), float(getattr(table, 'dmx_floor', 0.0)),
                 _stream()), 'dmx_estep')
         return logits, post, singlets

@@ -59,7 +59,8 @@ int dmx_unpack_match_calls(const uint8_t* snp_calls_packed, int64_t n_calls,
  *     variant_offsets int64 [n_variants + 1]
  *   the same rows stably re-sorted by barcode                              ["CSR", used by the E-step]:
  *     csr_variant, csr_e, csr_row (index of the row in CSC order), barcode_offsets int64 [n_barcodes + 1]
- *   n_mol_per_variant int64 [n_variants] = matched molecule-level calls per variant (demux.py:381)
+ *   n_mol_per_variant int64 [n_variants] = matched molecule-level calls per variant (demux.py:381); may be
+ *     NULL when the data prior is not needed (predict_posteriors)
  * Only calls whose barcode lies in [barcode_lo, barcode_hi) become rows (barcode sharding across GPUs; pass
  * 0, n_barcodes for everything); n_mol_per_variant always counts every matched call.
  * Synchronises `stream` once to return *h_n_rows and *h_n_matched on the host.

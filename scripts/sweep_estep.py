@@ -26,7 +26,7 @@ print(f'G={G} C={C} B={pack.n_barcodes} R={pack.n_rows} updates={pack.n_rows * C
 
 
 def run(env, reps=5):
-    for k in ('DMX_RG', 'DMX_FLUSHES', 'DMX_FLUSH_ROWS', 'DMX_PACKED', 'DMX_MAX_THREADS'):
+    for k in ('DMX_RG', 'DMX_FLUSHES', 'DMX_FLUSH_ROWS', 'DMX_MAX_THREADS', 'DMX_MIN_BLOCKS', 'DMX_INT_WIDEN'):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     buffers = {}
@@ -44,11 +44,9 @@ def run(env, reps=5):
 
 
 base = None
-rgs = [0, 2, 3, 5, 7] if G <= 40 else [0]
-for rg, max_threads, flushes, flush_rows in itertools.product(rgs, [128, 256], [1, 2], [8, 16]):
-    env = dict(DMX_FLUSHES=flushes, DMX_FLUSH_ROWS=flush_rows, DMX_MAX_THREADS=max_threads, DMX_VERBOSE=1)
-    if rg:
-        env['DMX_RG'] = rg
+grid = dict(DMX_MIN_BLOCKS=[2, 3], DMX_INT_WIDEN=[0, 1], DMX_FLUSH_ROWS=[16], DMX_FLUSHES=[1, 2])
+for combo in itertools.product(*grid.values()):
+    env = dict(zip(grid.keys(), combo), DMX_VERBOSE=0)
     try:
         best, mean, logits = run(env)
     except Exception as exc:  # noqa: BLE001
@@ -57,5 +55,5 @@ for rg, max_threads, flushes, flush_rows in itertools.product(rgs, [128, 256], [
     if base is None:
         base = logits
     diff = (logits.double() - base.double()).abs().max().item()
-    print(f'{env}  best {best:.3f} ms  mean {mean:.3f} ms  {pack.n_rows * C / best / 1e9:.1f} G upd/s  '
+    print(f'{env}  best {best:.3f} ms  mean {mean:.3f} ms  {pack.n_rows * C / best / 1e9:.2f} T upd/s  '
           f'max|dlogit| vs first {diff:.2e}')

@@ -160,7 +160,8 @@ def test_learn_genotypes_vs_reference_fixture(D, name, flavour):
 
 
 def test_m_step_bit_exact_given_identical_posteriors(D):
-    """With the oracle's posteriors as input the M-step is the same float64 sum in the same order: bit-exact."""
+    """With the oracle's posteriors as input the M-step adds the same float32 terms in float64 (row groups are
+    re-associated, which only matters within 1e-16 of a float32 rounding boundary): bit-exact in practice."""
     import torch
     case = load_case('g12_dp35')
     G, V = case.genotypes.n_genotypes, case.genotypes.n_variants
@@ -302,7 +303,7 @@ def test_barcode_sharding_is_consistent(D):
         from demuxalot_b200 import _native
         lib = _native.load()
         assert lib.dmx_mstep(h.variant_offsets.data_ptr(), h.csc_cb.data_ptr(), h.csc_e.data_ptr(), fs.data_ptr(),
-                             full.n_genotypes, full.n_genotypes, 2.0, out32.data_ptr(), full.n_genotypes,
+                             fs.shape[1], full.n_genotypes, 2.0, out32.data_ptr(), full.n_genotypes,
                              out64.data_ptr(), full.n_genotypes, 0, full.n_variants,
                              torch.cuda.current_stream().cuda_stream) == 0
         parts64.append(out64)
