@@ -61,49 +61,54 @@ def flatten_inputs(ds, run) -> dict:
     return out
 
 
+def make_case(ref, name: str, ds, run: dict) -> None:
+    """Runs the reference on one dataset (anything with .genotypes / .calls / .barcode_handler) and stores the fixture."""
+    R = ref.Demultiplexer
+    ds.genotypes.default_prior = run['default_prior']
+    dp, clip, n_it = run['doublet_prior'], run['p_genotype_clip'], run['n_iterations']
+    fx = flatten_inputs(ds, run)
+    fx['doublet_prior'], fx['p_genotype_clip'], fx['n_iterations'] = np.float64(dp), np.float64(clip), np.int64(n_it)
+
+    v2s, betas_learn, mol, rows = R.pack_calls(ds.calls, ds.genotypes, add_data_prior=True)
+    _, betas_predict, _, _ = R.pack_calls(ds.calls, ds.genotypes, add_data_prior=False)
+    fx['variant2snp'] = v2s
+    fx['betas_reg_learn'], fx['betas_reg_predict'] = betas_learn, betas_predict
+    fx['mol_variant_id'] = mol['variant_id']
+    for field in ('variant_id', 'snp_id', 'compressed_cb', 'p_base_wrong', 'barcode_variant_count'):
+        fx[f'rows_{field}'] = np.asarray(rows[field])
+    fx['table_predict'] = R._compute_probs_from_betas(v2s, betas_predict, p_genotype_clip=clip)
+
+    logits_df, probs_df = R.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler,
+                                               p_genotype_clip=clip, doublet_prior=dp)
+    fx['predict_logits'], fx['predict_post'] = logits_df.values, probs_df.values
+    fx['columns'] = np.array(list(logits_df.columns))
+
+    prior = None
+    if run['prior']:
+        rng = np.random.default_rng(7)
+        prior = (rng.normal(size=logits_df.shape) * 2).astype(np.float32).astype(np.float64)
+        prior[rng.random(len(prior)) < 0.2, 0] += 100.  # "labelled" barcodes as in tests/test_synthetic.py:225
+        fx['prior_logits'] = prior
+    stages = list(R.staged_genotype_learning(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it,
+                                             p_genotype_clip=clip, doublet_prior=dp, barcode_prior_logits=prior))
+    fx['stage_logits'] = np.stack([dbg['barcode_logits'] for _, dbg in stages])
+    fx['stage_post'] = np.stack([df.values for df, _ in stages])
+    fx['stage_addition'] = np.stack([dbg['genotype_addition'] for _, dbg in stages])
+    learnt, post_df = R.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it,
+                                        p_genotype_clip=clip, doublet_prior=dp, barcode_prior_logits=prior)
+    fx['learnt_betas'], fx['learn_post'] = np.array(learnt.get_betas()), post_df.values
+    path = HERE / f'{name}.npz'
+    np.savez_compressed(path, **fx)
+    print(f'{name}: V={len(v2s)} rows={len(rows)} matched={len(mol)} C={logits_df.shape[1]} '
+          f'-> {path.name} ({path.stat().st_size / 1024:.0f} KiB)')
+
+
 def main() -> None:
     ref = load_reference()
     assert ref is not None, '/root/reference is required to generate golden vectors'
     R = ref.Demultiplexer
     for name, (gen, run) in CASES.items():
-        ds = make_dataset(**gen)
-        ds.genotypes.default_prior = run['default_prior']
-        dp, clip, n_it = run['doublet_prior'], run['p_genotype_clip'], run['n_iterations']
-        fx = flatten_inputs(ds, run)
-        fx['doublet_prior'], fx['p_genotype_clip'], fx['n_iterations'] = np.float64(dp), np.float64(clip), np.int64(n_it)
-
-        v2s, betas_learn, mol, rows = R.pack_calls(ds.calls, ds.genotypes, add_data_prior=True)
-        _, betas_predict, _, _ = R.pack_calls(ds.calls, ds.genotypes, add_data_prior=False)
-        fx['variant2snp'] = v2s
-        fx['betas_reg_learn'], fx['betas_reg_predict'] = betas_learn, betas_predict
-        fx['mol_variant_id'] = mol['variant_id']
-        for field in ('variant_id', 'snp_id', 'compressed_cb', 'p_base_wrong', 'barcode_variant_count'):
-            fx[f'rows_{field}'] = np.asarray(rows[field])
-        fx['table_predict'] = R._compute_probs_from_betas(v2s, betas_predict, p_genotype_clip=clip)
-
-        logits_df, probs_df = R.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler,
-                                                   p_genotype_clip=clip, doublet_prior=dp)
-        fx['predict_logits'], fx['predict_post'] = logits_df.values, probs_df.values
-        fx['columns'] = np.array(list(logits_df.columns))
-
-        prior = None
-        if run['prior']:
-            rng = np.random.default_rng(7)
-            prior = (rng.normal(size=logits_df.shape) * 2).astype(np.float32).astype(np.float64)
-            prior[rng.random(len(prior)) < 0.2, 0] += 100.  # "labelled" barcodes as in tests/test_synthetic.py:225
-            fx['prior_logits'] = prior
-        stages = list(R.staged_genotype_learning(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it,
-                                                 p_genotype_clip=clip, doublet_prior=dp, barcode_prior_logits=prior))
-        fx['stage_logits'] = np.stack([dbg['barcode_logits'] for _, dbg in stages])
-        fx['stage_post'] = np.stack([df.values for df, _ in stages])
-        fx['stage_addition'] = np.stack([dbg['genotype_addition'] for _, dbg in stages])
-        learnt, post_df = R.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it,
-                                            p_genotype_clip=clip, doublet_prior=dp, barcode_prior_logits=prior)
-        fx['learnt_betas'], fx['learn_post'] = np.array(learnt.get_betas()), post_df.values
-        path = HERE / f'{name}.npz'
-        np.savez_compressed(path, **fx)
-        print(f'{name}: V={len(v2s)} rows={len(rows)} matched={len(mol)} C={logits_df.shape[1]} '
-              f'-> {path.name} ({path.stat().st_size / 1024:.0f} KiB)')
+        make_case(ref, name, make_dataset(**gen), run)
 
     # known-answer table for the doublet prior (reference tests/test_utils.py:34-40)
     kat = {}

@@ -9,7 +9,8 @@ import numpy as np
 from demuxalot_b200 import BarcodeHandler, CompressedSNPCalls, ProbabilisticGenotypes
 
 GOLDEN_DIR = Path(__file__).resolve().parent / 'golden'
-CASES = ['g4_dp25', 'g7_dp0_prior', 'g12_dp35', 'g33_dp35_lowdepth']
+# synthetic cases (make_golden.py) + config #1: the reference's bundled example, first 48 barcodes (make_example_fixture.py)
+CASES = ['g4_dp25', 'g7_dp0_prior', 'g12_dp35', 'g33_dp35_lowdepth', 'example_data_48bc']
 
 
 def load_case(name: str) -> SimpleNamespace:

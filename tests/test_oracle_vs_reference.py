@@ -83,3 +83,20 @@ def test_our_host_types_feed_the_reference_and_parquet_roundtrip(tmp_path):
     back.add_prior_betas(tmp_path / 'theirs.parquet')
     for key, vid in ours.var2varid.items():
         assert np.array_equal(ours.variant_betas[vid], back.variant_betas[back.var2varid[key]])
+
+
+def test_plain_text_add_vcf_matches_reference_on_example_data():
+    """Our pysam-free `add_vcf` builds the same genotypes as the reference's (pysam.VariantFile) on the bundled VCF;
+    the expected values were written by the reference through tests/pysam_shim.py (make_example_fixture.py)."""
+    from pathlib import Path
+    from demuxalot_b200 import ProbabilisticGenotypes
+    from golden_io import GOLDEN_DIR
+    vcf = Path('/root/reference/examples/example_data/test_genotypes.vcf')
+    want = np.load(GOLDEN_DIR / 'example_genotypes.npz')
+    ours = ProbabilisticGenotypes(['Donor01', 'Donor02', 'Donor03', 'Donor04'])
+    ours.add_vcf(vcf)
+    keys = [(str(c), int(p), str(b)) for c, p, b in zip(want['var_chrom'], want['var_pos'], want['var_base'])]
+    assert list(ours.var2varid.items()) == list(zip(keys, [int(v) for v in want['var_id']]))
+    assert np.array_equal(bits(np.array(ours.get_betas())), bits(want['betas']))
+    positions = ours.get_chromosome2positions()
+    assert sorted(positions) == ['chr1', 'chr2', 'chr3'] and sum(len(p) for p in positions.values()) == 1212
