@@ -363,9 +363,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             'alu': {
                 'updates_per_s': R * C / kernel_s,
                 'updates_per_clk_per_sm': R * C / kernel_s / (sm_count * sm_mhz * 1e6),
-                'fp32_lanes_per_clk_per_sm': 128,
-                'min_fp32_ops_per_update': 2,
-                'frac_of_fp32_issue': 2 * R * C / kernel_s / (sm_count * 128 * sm_mhz * 1e6),
+                # measured on this GPU type with scripts/microbench_fp32x2.cu (profiles/r01_microbench.log): a
+                # dependent FADD2 -> FMUL2 pair stream issues 2.27 warp-instructions/clk/SM = 72.6 updates/clk/SM
+                'issue_ceiling_updates_per_clk_per_sm': 72.6,
+                'frac_of_issue_ceiling': R * C / kernel_s / (sm_count * sm_mhz * 1e6) / 72.6,
             },
         },
         'em': {'iterations_per_s': args.steps / (em_total_ms / 1e3), 'ms_per_iteration': em_total_ms / args.steps,
