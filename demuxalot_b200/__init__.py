@@ -9,6 +9,7 @@ fallback (build the library with `python -m demuxalot_b200.build`).
 """
 from .barcodes import BarcodeHandler
 from .calls import CompressedSNPCalls
+from .counting import count_snps
 from .genotype_store import ProbabilisticGenotypes
 
 __version__ = '0.1.0'
@@ -22,4 +23,4 @@ def __getattr__(name):
     raise AttributeError(f'module {__name__!r} has no attribute {name!r}')
 
 
-__all__ = ['BarcodeHandler', 'CompressedSNPCalls', 'Demultiplexer', 'ProbabilisticGenotypes']
+__all__ = ['BarcodeHandler', 'CompressedSNPCalls', 'Demultiplexer', 'ProbabilisticGenotypes', 'count_snps']
