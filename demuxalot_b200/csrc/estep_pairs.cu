@@ -16,9 +16,11 @@
 //     (variant, p_base_wrong) are prefetched into registers one chunk ahead; each thread finishes the pieces it
 //     copied itself (a = fma(P, 1-e, e') for FAST), so one __syncthreads per stage is enough;
 //   * FAST inner loop: packed f32x2 adds/multiplies (FADD2 / FMUL2 on sm_100, the scalar operand is broadcast
-//     by the instruction), FLUSH_ROWS row factors multiplied per product, one raw lg2.approx per product,
-//     float64 accumulation.  Factors are 2x the reference argument (a_i + a_j); the 1/2 per row is removed
-//     exactly in the epilogue.  Padding rows are staged as a = 1 (factor 2, log2 = 1) and cancel there too.
+//     by the instruction) keep a running float32 product per pair; every FLUSH_ROWS rows the binary exponent
+//     of each product is moved into an integer sum and the mantissa reset to [1, 2) (exact; 3 ALU instructions),
+//     so the loop contains no MUFU and no FP64 at all and one lg2 per pair is taken at the very end.  Factors
+//     are 2x the reference argument (a_i + a_j); the 1/2 per row is removed exactly in the epilogue.  Padding
+//     rows are staged as a = 1 (factor 2, log2 = 1) and cancel there too.
 #include "common.cuh"
 
 namespace dmx {
@@ -77,8 +79,9 @@ __device__ __forceinline__ float lg2_raw(float x) {
 }
 
 // Variants measured and dropped (scripts/sweep_estep.py, profiles/): 8x4 tiles (168 registers, same speed),
-// __launch_bounds__(256, 3) (80 registers, spills, 15-30 % slower), an integer float->double widening to take
-// F2F off the XU pipe (no gain), scalar FADD/FMUL instead of the packed forms (8-10 % slower).
+// __launch_bounds__(256, 3) (80 registers: no faster even without spills -- the kernel is not occupancy bound),
+// one lg2 + float64 add per 16-row product instead of the integer exponent bookkeeping (3-6 % slower), scalar
+// FADD/FMUL instead of the packed forms (8-10 % slower).
 template <int FLAVOUR, int FLUSH_ROWS>
 __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const PairsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -113,11 +116,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
     const int64_t row_hi = p.offsets[barcode + 1];
     const int n_chunks = (int)((row_hi - row_lo + chunk_rows - 1) / chunk_rows);
 
-    double acc[TILE][TILE];
+    double acc[TILE][TILE];          // EXACT: running float64 sums; FAST: filled once after the row loop
+    uint64_t prod[TILE / 2][TILE];   // FAST: running products (packed float32 pairs), mantissas kept in [1, 2)
+    int esum[TILE][TILE];            // FAST: biased binary exponents moved out of the products
 #pragma unroll
     for (int a = 0; a < TILE; ++a)
 #pragma unroll
-        for (int b = 0; b < TILE; ++b) acc[a][b] = 0.0;
+        for (int b = 0; b < TILE; ++b) { acc[a][b] = 0.0; esum[a][b] = 0; }
+#pragma unroll
+    for (int a = 0; a < TILE / 2; ++a)
+#pragma unroll
+        for (int b = 0; b < TILE; ++b) prod[a][b] = pack2(1.f, 1.f);
 
     // ---- staging -----------------------------------------------------------------------------------------------
     // A slot = up to QPT consecutive 16-byte quads of one staged row (a whole row for G <= 32); thread t owns the
@@ -248,11 +257,6 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
                 const float* rows = cur + (f * FLUSH_ROWS * p.row_groups + rg) * ld;
                 const int row_stride = p.row_groups * ld;
                 if (FLAVOUR == DMX_ESTEP_FAST) {
-                    uint64_t prod[TILE / 2][TILE];
-#pragma unroll
-                    for (int a = 0; a < TILE / 2; ++a)
-#pragma unroll
-                        for (int b = 0; b < TILE; ++b) prod[a][b] = pack2(1.f, 1.f);
 #pragma unroll
                     for (int k = 0; k < FLUSH_ROWS; ++k) {
                         const float* s = rows + k * row_stride;
@@ -266,14 +270,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
                             for (int b = 0; b < TILE; ++b)
                                 prod[a][b] = mul2(prod[a][b], add2(a2[a], pack2(aj[b], aj[b])));
                     }
+                    // renormalise: move the binary exponent of every running product into an integer sum and keep
+                    // the mantissa in [1, 2) -- exact, three ALU instructions per product, no MUFU / FP64 in the loop
 #pragma unroll
                     for (int a = 0; a < TILE / 2; ++a)
 #pragma unroll
                         for (int b = 0; b < TILE; ++b) {
                             float lo, hi;
                             unpack2(prod[a][b], lo, hi);
-                            acc[2 * a][b] += (double)lg2_raw(lo);
-                            acc[2 * a + 1][b] += (double)lg2_raw(hi);
+                            const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
+                            esum[2 * a][b] += (int)(blo >> 23);
+                            esum[2 * a + 1][b] += (int)(bhi >> 23);
+                            prod[a][b] = pack2(__uint_as_float((blo & 0x007fffffu) | 0x3f800000u),
+                                               __uint_as_float((bhi & 0x007fffffu) | 0x3f800000u));
                         }
                 } else {
 #pragma unroll 4
@@ -299,6 +308,20 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
 
         if (more) land(nxt);
         __syncthreads();
+    }
+
+    if (FLAVOUR == DMX_ESTEP_FAST) {
+        // log2 of the row group's product = (sum of unbiased exponents) + log2(mantissa in [1, 2))
+        const int bias = 127 * n_chunks * p.flushes;
+#pragma unroll
+        for (int a = 0; a < TILE / 2; ++a)
+#pragma unroll
+            for (int b = 0; b < TILE; ++b) {
+                float lo, hi;
+                unpack2(prod[a][b], lo, hi);
+                acc[2 * a][b] = (double)(esum[2 * a][b] - bias) + (double)lg2_raw(lo);
+                acc[2 * a + 1][b] = (double)(esum[2 * a + 1][b] - bias) + (double)lg2_raw(hi);
+            }
     }
 
     // ---- fixed-order reduction over the row groups (deterministic) ---------------------------------------------

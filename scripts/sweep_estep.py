@@ -44,7 +44,7 @@ def run(env, reps=5):
 
 
 base = None
-grid = dict(DMX_MIN_BLOCKS=[2, 3], DMX_INT_WIDEN=[0, 1], DMX_FLUSH_ROWS=[16], DMX_FLUSHES=[1, 2])
+grid = dict(DMX_MIN_BLOCKS=[2, 3], DMX_MAX_THREADS=[128, 256], DMX_FLUSH_ROWS=[8, 16], DMX_FLUSHES=[1, 2])
 for combo in itertools.product(*grid.values()):
     env = dict(zip(grid.keys(), combo), DMX_VERBOSE=0)
     try:
