@@ -32,7 +32,7 @@ constexpr float ERROR_FLOOR = 1e-4f;
 // estep_pairs.cu
 int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant, const float* csr_e,
                        int64_t n_barcodes, const float* table, int64_t ld_table, int G, double doublet_prior,
-                       float table_floor, const float* prior_logits, int64_t ld_prior, float* logits,
+                       float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
                        int64_t ld_logits, int flavour, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __re
                                                              const int32_t* __restrict__ variant,
                                                              const float* __restrict__ e_arr,
                                                              const float* __restrict__ table, int64_t ld_table,
-                                                             int n_genotypes, const float* __restrict__ prior,
+                                                             int n_genotypes, const double* __restrict__ prior,
                                                              int64_t ld_prior, float* __restrict__ logits,
                                                              int64_t ld_logits) {
     constexpr int RGW = 32 / LPR;                  // rows a warp processes at once
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __re
                     const double sum = ((partial[0][s * 4 + c][lane] + partial[1][s * 4 + c][lane]) +
                                         partial[2][s * 4 + c][lane]) + partial[3][s * 4 + c][lane];
                     float logit = (float)(0.0 + sum);
-                    if (prior) logit = (float)((double)logit + (double)prior[barcode * ld_prior + g]);
+                    if (prior) logit = (float)((double)logit + prior[barcode * ld_prior + g]);
                     logits[barcode * ld_logits + g] = logit;
                 }
             }
@@ -196,7 +196,7 @@ static int launch_softmax(const float* logits, int64_t ld_logits, int64_t n_rows
 template <int FLAVOUR>
 static int launch_singlets(unsigned grid, cudaStream_t stream, const int64_t* offsets, const int32_t* order,
                            const int32_t* variant, const float* e, const float* table, int64_t ld_table, int G,
-                           const float* prior, int64_t ld_prior, float* logits, int64_t ld_logits) {
+                           const double* prior, int64_t ld_prior, float* logits, int64_t ld_logits) {
     const int quads = (int)(ld_table / 4);
 #define DMX_SINGLETS(LPR, SLOTS)                                                                                  \
     estep_singlets_kernel<FLAVOUR, LPR, SLOTS><<<grid, 128, 0, stream>>>(offsets, order, variant, e, table, ld_table, \
@@ -234,7 +234,7 @@ int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int
 int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant,
               const float* csr_e, int64_t n_barcodes,
               const float* table, int64_t ld_table, int32_t n_genotypes, double doublet_prior,
-              const float* prior_logits, int64_t ld_prior, float* logits, int64_t ld_logits, float* posteriors,
+              const double* prior_logits, int64_t ld_prior, float* logits, int64_t ld_logits, float* posteriors,
               int64_t ld_post, float* singlet_posteriors, int64_t ld_singlet, void* workspace,
               int64_t workspace_bytes, int32_t flavour, float table_floor, void* stream_) {
     using namespace dmx;

@@ -47,7 +47,7 @@ struct PairsParams {
     int flushes;        // products per row group and staged chunk
     int ld_smem;        // floats per staged row (gp + 4)
     float doublet_bonus;
-    const float* prior;
+    const double* prior;  // float64, as numpy adds it: float32(float64(logit) + prior), demux.py:99
     int64_t ld_prior;
     float* logits;
     int64_t ld_logits;
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
                     if (FLAVOUR == DMX_ESTEP_FAST) sum = (sum - padded_rows) * 0.693147180559945309417232;
                     const float pen = (i == j) ? 0.f : p.doublet_bonus;
                     float logit = (float)((double)pen + sum);
-                    if (p.prior) logit = (float)((double)logit + (double)p.prior[barcode * p.ld_prior + col]);
+                    if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
                     p.logits[barcode * p.ld_logits + col] = logit;
                 }
             }
@@ -399,7 +399,7 @@ static int launch_variant(const PairsParams& p, unsigned grid, int threads, size
 // Tuning overrides (experiments only): DMX_RG, DMX_FLUSHES, DMX_FLUSH_ROWS, DMX_MAX_THREADS, DMX_VERBOSE.
 int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant, const float* csr_e,
                        int64_t n_barcodes, const float* table, int64_t ld_table, int G, double doublet_prior,
-                       float table_floor, const float* prior_logits, int64_t ld_prior, float* logits,
+                       float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
                        int64_t ld_logits, int flavour, cudaStream_t stream) {
     PairsParams p;
     p.offsets = barcode_offsets;

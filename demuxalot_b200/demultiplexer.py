@@ -418,7 +418,7 @@ class Demultiplexer:
         if barcode_prior_logits is None:
             return None
         assert barcode_prior_logits.shape == (n_barcodes, n_cols), 'wrong shape of priors'
-        return _to_device(np.asarray(barcode_prior_logits, dtype=np.float32), dev)
+        return _to_device(np.ascontiguousarray(barcode_prior_logits, dtype=np.float64), dev)
 
     @classmethod
     def staged_genotype_learning(cls, chromosome2compressed_snp_calls, genotypes, barcode_handler,

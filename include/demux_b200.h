@@ -106,7 +106,8 @@ int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addi
 /* ---- (a7-a10) E-step: demux.py:246-265, 158-191, 97-101 ----------------------------------------------
  * logits[b, c] = float32(pen[c] + sum_{rows r of b} log(p_c[v_r] (1 - e_r) + max(e_r, 1e-4))), columns:
  * G singlets then (doublet_prior != 0) the G(G-1)/2 pairs i < j, i-major.  Optional prior_logits [B, C]
- * (float32) is added after the sum (demux.py:97-99).  Then a row softmax (float32).
+ * (float64, combined as numpy does: float32(float64(logit) + prior)) is added after the sum (demux.py:97-99).
+ * Then a row softmax (float32).
  * Outputs (each may be NULL): logits [B, ld_logits], posteriors [B, ld_post], singlet posteriors
  * [B, ld_singlet] (first G columns of the softmax; the only part the M-step reads, demux.py:115).
  * `table` is the output of dmx_probs_from_betas with ld_table a multiple of 4.
@@ -118,7 +119,7 @@ int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, doubl
 int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order /* dmx_barcode_schedule, or NULL */,
               const int32_t* csr_variant, const float* csr_e, int64_t n_barcodes,
               const float* table, int64_t ld_table, int32_t n_genotypes,
-              double doublet_prior, const float* prior_logits, int64_t ld_prior,
+              double doublet_prior, const double* prior_logits, int64_t ld_prior,
               float* logits, int64_t ld_logits, float* posteriors, int64_t ld_post,
               float* singlet_posteriors, int64_t ld_singlet,
               void* workspace, int64_t workspace_bytes, int32_t flavour, float table_floor, void* stream);

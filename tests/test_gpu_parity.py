@@ -310,3 +310,22 @@ def test_barcode_sharding_is_consistent(D):
     whole = D._m_step(full, fs).cpu().numpy()
     summed = (parts64[0] + parts64[1]).to(torch.float32).cpu().numpy()
     assert np.abs(summed.astype(np.float64) - whole).max() <= 1e-6 * max(1.0, np.abs(whole).max())
+
+
+@pytest.mark.parametrize('dp', [0., 0.35])
+def test_float64_prior_logits_are_added_like_numpy(D, dp):
+    """barcode_prior_logits that are not float32-representable: the reference computes float32(float64(logit) + prior)."""
+    case = load_case('g7_dp0_prior')
+    rng = np.random.default_rng(3)
+    n_cols = len(oracle.option_names(case.genotypes.genotype_names, dp))
+    prior = rng.normal(size=(case.barcode_handler.n_barcodes, n_cols)) * 0.1 + 1 / 3
+    D.estep_flavour = 'exact'
+    try:
+        got = list(D.staged_genotype_learning(case.calls, case.genotypes, case.barcode_handler, n_iterations=1,
+                                              doublet_prior=dp, barcode_prior_logits=prior))[0][1]['barcode_logits']
+        base = list(D.staged_genotype_learning(case.calls, case.genotypes, case.barcode_handler, n_iterations=1,
+                                               doublet_prior=dp))[0][1]['barcode_logits']
+    finally:
+        D.estep_flavour = 'fast'
+    want = (base.astype(np.float64) + prior).astype(np.float32)  # numpy's in-place `logits += prior`
+    assert np.array_equal(bits(got), bits(want))
