@@ -4,22 +4,13 @@
 //
 //   L[b, c] = float32( pen[c] + sum_{rows r of barcode b}^{float64} log( p_c[v_r] (1 - e_r) + max(e_r, 1e-4) ) )
 //
-// Two kernels:
-//   * estep_pairs_kernel  (doublet_prior != 0): "log-semiring SYRK".  The G(G+1)/2 columns of a barcode are the
-//     upper triangle (diagonal = singlets) of a G x G pair matrix; each thread owns an 8 x 4 register tile of it
-//     and walks the barcode's rows, whose table rows P[v_r, :] are staged in shared memory with cp.async
-//     (double buffered).  Row groups split a barcode's rows inside the CTA and are reduced in a fixed order
-//     (no atomics -> deterministic).  Bound: FP32 issue / MUFU, not HBM (0.26 B per update at G = 32).
-//   * estep_singlets_kernel (doublet_prior == 0): lanes over genotypes, warps over rows; HBM / L2-gather bound.
+// This file: the singlet-only kernel (doublet_prior == 0), the row softmax and the dmx_estep entry point.
+// The pair kernel for doublet_prior != 0 lives in estep_pairs.cu.
 //
-// Arithmetic flavours (DMX_ESTEP_*):
-//   EXACT  x = fl(fl(fl(P_i + P_j) * (0.5 (1-e))) + e'), t = logf(x) (float32), float64 accumulation: the
-//          reference's per-term roundings (0.5 scaling is exact, so folding it into (1-e) changes nothing).
-//   FAST   a_g = fma(P_g, 1-e, e') once per row and genotype, x = a_i + a_j (= 2x the reference argument up to
-//          one rounding), products of 8 consecutive row factors in float32 (every factor is in [2e-4, 2.0002], so
-//          no under/overflow), one lg2.approx per product, float64 accumulation, the factor 1/2 per row removed
-//          exactly at the end.  More accurate than summing rounded logs; differs from numpy by less than
-//          numpy's own float32 log error (tests/test_gpu_parity.py reports the distribution).
+// Arithmetic flavours (DMX_ESTEP_*) of the singlet kernel:
+//   EXACT  x = fl(fl(P_g * (1-e)) + e'), t = logf(x) (float32), float64 accumulation: the reference's roundings.
+//   FAST   x = fma(P_g, 1-e, e'), products of 8 consecutive row factors in float32 (every factor is in
+//          [1e-4, 1.0001], so a product stays a normal number), one lg2.approx per product, float64 accumulation.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -30,8 +21,9 @@ constexpr int FLUSH_ROWS = 8;  // row factors multiplied before one lg2 (singlet
 constexpr float ERROR_FLOOR = 1e-4f;
 
 // estep_pairs.cu
-int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant, const float* csr_e,
-                       int64_t n_barcodes, const float* table, int64_t ld_table, int G, double doublet_prior,
+int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant,
+                       const float* csr_e, int64_t n_barcodes, const float* table, int64_t ld_table, int G,
+                       double doublet_prior,
                        float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
                        int64_t ld_logits, int flavour, cudaStream_t stream);
 

@@ -397,8 +397,9 @@ static int launch_variant(const PairsParams& p, unsigned grid, int threads, size
 // table_floor: lower bound of the table entries (the clip of demux.py:274), 0 if unknown.  It decides how many
 // row factors (>= 2 (table_floor + 1e-4) each) can be multiplied in float32 without leaving the normal range.
 // Tuning overrides (experiments only): DMX_RG, DMX_FLUSHES, DMX_FLUSH_ROWS, DMX_MAX_THREADS, DMX_VERBOSE.
-int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant, const float* csr_e,
-                       int64_t n_barcodes, const float* table, int64_t ld_table, int G, double doublet_prior,
+int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant,
+                       const float* csr_e, int64_t n_barcodes, const float* table, int64_t ld_table, int G,
+                       double doublet_prior,
                        float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
                        int64_t ld_logits, int flavour, cudaStream_t stream) {
     PairsParams p;
