@@ -25,7 +25,7 @@
 
 namespace dmx {
 
-constexpr int TILE = 4;        // thread tile: 4 (i) x 4 (j) pairs
+constexpr int TILE = 4;        // thread tile: 4 (i) x TJ (j) pairs, TJ = 4 or 8 (template parameter)
 constexpr int MAX_PASSES = 2;  // staging slots per thread and chunk
 constexpr int QPT = 8;         // 16-byte quads per staging slot
 constexpr int MAX_THREADS = 256;
@@ -82,7 +82,7 @@ __device__ __forceinline__ float lg2_raw(float x) {
 // __launch_bounds__(256, 3) (80 registers: no faster even without spills -- the kernel is not occupancy bound),
 // one lg2 + float64 add per 16-row product instead of the integer exponent bookkeeping (3-6 % slower), scalar
 // FADD/FMUL instead of the packed forms (8-10 % slower).
-template <int FLAVOUR, int FLUSH_ROWS>
+template <int FLAVOUR, int FLUSH_ROWS, int TJ>
 __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const PairsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
@@ -96,14 +96,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
     const int tile = cta_in_barcode * p.tiles_per_cta + tile_local;
     const bool has_tile = tile < p.n_tiles && rg < p.row_groups;  // CTAs may carry staging-only threads
 
-    // tile -> (i0, j0): tiles are enumerated i-block major; i-block pi owns the j-blocks pi .. gp/4 - 1
+    // tile -> (i0, j0): tiles are enumerated i-block major; i-block pi (4 wide) owns the j-blocks (TJ wide) that
+    // reach the diagonal or lie above it: 4 pi / TJ .. gp / TJ - 1
     int i0 = 0, j0 = 0;
     {
-        const int q_total = p.gp / TILE;
+        const int q_total = p.gp / TJ;
         int t = has_tile ? tile : 0, pi = 0;
-        while (t >= q_total - pi) { t -= q_total - pi; ++pi; }
+        while (t >= q_total - (pi * TILE) / TJ) { t -= q_total - (pi * TILE) / TJ; ++pi; }
         i0 = pi * TILE;
-        j0 = (pi + t) * TILE;
+        j0 = ((pi * TILE) / TJ + t) * TJ;
     }
 
     const int chunk_rows = p.row_groups * p.flushes * FLUSH_ROWS;
@@ -116,17 +117,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
     const int64_t row_hi = p.offsets[barcode + 1];
     const int n_chunks = (int)((row_hi - row_lo + chunk_rows - 1) / chunk_rows);
 
-    double acc[TILE][TILE];          // EXACT: running float64 sums; FAST: filled once after the row loop
-    uint64_t prod[TILE / 2][TILE];   // FAST: running products (packed float32 pairs), mantissas kept in [1, 2)
-    int esum[TILE][TILE];            // FAST: biased binary exponents moved out of the products
+    double acc[TILE][TJ];          // EXACT: running float64 sums; FAST: filled once after the row loop
+    uint64_t prod[TILE / 2][TJ];   // FAST: running products (packed float32 pairs), mantissas kept in [1, 2)
+    int esum[TILE][TJ];            // FAST: biased binary exponents moved out of the products
 #pragma unroll
     for (int a = 0; a < TILE; ++a)
 #pragma unroll
-        for (int b = 0; b < TILE; ++b) { acc[a][b] = 0.0; esum[a][b] = 0; }
+        for (int b = 0; b < TJ; ++b) { acc[a][b] = 0.0; esum[a][b] = 0; }
 #pragma unroll
     for (int a = 0; a < TILE / 2; ++a)
 #pragma unroll
-        for (int b = 0; b < TILE; ++b) prod[a][b] = pack2(1.f, 1.f);
+        for (int b = 0; b < TJ; ++b) prod[a][b] = pack2(1.f, 1.f);
 
     // ---- staging -----------------------------------------------------------------------------------------------
     // A slot = up to QPT consecutive 16-byte quads of one staged row (a whole row for G <= 32); thread t owns the
@@ -261,13 +262,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
                     for (int k = 0; k < FLUSH_ROWS; ++k) {
                         const float* s = rows + k * row_stride;
                         const float4 ai = *reinterpret_cast<const float4*>(s + i0);
-                        const float4 bj = *reinterpret_cast<const float4*>(s + j0);
                         const uint64_t a2[TILE / 2] = {pack2(ai.x, ai.y), pack2(ai.z, ai.w)};
-                        const float aj[TILE] = {bj.x, bj.y, bj.z, bj.w};
+                        float aj[TJ];
+#pragma unroll
+                        for (int q = 0; q < TJ / 4; ++q) {
+                            const float4 bj = *reinterpret_cast<const float4*>(s + j0 + 4 * q);
+                            aj[4 * q] = bj.x; aj[4 * q + 1] = bj.y; aj[4 * q + 2] = bj.z; aj[4 * q + 3] = bj.w;
+                        }
 #pragma unroll
                         for (int a = 0; a < TILE / 2; ++a)
 #pragma unroll
-                            for (int b = 0; b < TILE; ++b)
+                            for (int b = 0; b < TJ; ++b)
                                 prod[a][b] = mul2(prod[a][b], add2(a2[a], pack2(aj[b], aj[b])));
                     }
                     // renormalise: move the binary exponent of every running product into an integer sum and keep
@@ -275,7 +280,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
 #pragma unroll
                     for (int a = 0; a < TILE / 2; ++a)
 #pragma unroll
-                        for (int b = 0; b < TILE; ++b) {
+                        for (int b = 0; b < TJ; ++b) {
                             float lo, hi;
                             unpack2(prod[a][b], lo, hi);
                             const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
@@ -289,15 +294,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
                     for (int k = 0; k < FLUSH_ROWS; ++k) {
                         const float* s = rows + k * row_stride;
                         const float4 ai = *reinterpret_cast<const float4*>(s + i0);
-                        const float4 bj = *reinterpret_cast<const float4*>(s + j0);
                         const float hw = s[p.gp];
                         const float ef = s[p.gp + 1];
                         const float pi[TILE] = {ai.x, ai.y, ai.z, ai.w};
-                        const float pj[TILE] = {bj.x, bj.y, bj.z, bj.w};
+                        float pj[TJ];
+#pragma unroll
+                        for (int q = 0; q < TJ / 4; ++q) {
+                            const float4 bj = *reinterpret_cast<const float4*>(s + j0 + 4 * q);
+                            pj[4 * q] = bj.x; pj[4 * q + 1] = bj.y; pj[4 * q + 2] = bj.z; pj[4 * q + 3] = bj.w;
+                        }
 #pragma unroll
                         for (int a = 0; a < TILE; ++a)
 #pragma unroll
-                            for (int b = 0; b < TILE; ++b) {
+                            for (int b = 0; b < TJ; ++b) {
                                 const float x = __fadd_rn(__fmul_rn(__fadd_rn(pi[a], pj[b]), hw), ef);
                                 acc[a][b] += (double)logf(x);
                             }
@@ -316,7 +325,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
 #pragma unroll
         for (int a = 0; a < TILE / 2; ++a)
 #pragma unroll
-            for (int b = 0; b < TILE; ++b) {
+            for (int b = 0; b < TJ; ++b) {
                 float lo, hi;
                 unpack2(prod[a][b], lo, hi);
                 acc[2 * a][b] = (double)(esum[2 * a][b] - bias) + (double)lg2_raw(lo);
@@ -331,8 +340,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
 #pragma unroll
                 for (int a = 0; a < TILE; ++a)
 #pragma unroll
-                    for (int b = 0; b < TILE; ++b) {
-                        double* slot = reduce_buf + (a * TILE + b) * p.tiles_per_cta + tile_local;
+                    for (int b = 0; b < TJ; ++b) {
+                        double* slot = reduce_buf + (a * TJ + b) * p.tiles_per_cta + tile_local;
                         if (g == 0) *slot = acc[a][b]; else *slot += acc[a][b];
                     }
             }
@@ -342,7 +351,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
 #pragma unroll
             for (int a = 0; a < TILE; ++a)
 #pragma unroll
-                for (int b = 0; b < TILE; ++b) acc[a][b] = reduce_buf[(a * TILE + b) * p.tiles_per_cta + tile_local];
+                for (int b = 0; b < TJ; ++b) acc[a][b] = reduce_buf[(a * TJ + b) * p.tiles_per_cta + tile_local];
         }
     }
 
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 2) estep_pairs_kernel(const Pairs
         for (int a = 0; a < TILE; ++a) {
             const int i = i0 + a;
 #pragma unroll
-            for (int b = 0; b < TILE; ++b) {
+            for (int b = 0; b < TJ; ++b) {
                 const int j = j0 + b;
                 if (i < G && j < G && j >= i) {
                     const int64_t col = (i == j) ? i : (int64_t)G + (int64_t)i * G - (int64_t)i * (i + 1) / 2 + (j - i - 1);
@@ -383,9 +392,9 @@ static int env_int(const char* name, int fallback) {
     return (v && *v) ? atoi(v) : fallback;
 }
 
-template <int FLAVOUR, int FLUSH_ROWS>
+template <int FLAVOUR, int FLUSH_ROWS, int TJ>
 static int launch_variant(const PairsParams& p, unsigned grid, int threads, size_t smem, cudaStream_t stream) {
-    auto kernel = estep_pairs_kernel<FLAVOUR, FLUSH_ROWS>;
+    auto kernel = estep_pairs_kernel<FLAVOUR, FLUSH_ROWS, TJ>;
     DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxShared));
@@ -410,9 +419,13 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
     p.table = table;
     p.ld_table = ld_table;
     p.n_genotypes = G;
-    p.gp = (int)round_up(G, TILE);
-    const int q_total = p.gp / TILE;
-    const int n_tiles = q_total * (q_total + 1) / 2;
+    // thread tile 4 x TJ: the wider tile reads 3 instead of 4 shared-memory vectors per 32 updates but wastes more
+    // lanes on the diagonal, so it pays off for many genotypes (measured: G = 200 yes, G = 32 no)
+    int tj = env_int("DMX_TJ", G >= 48 ? 8 : 4);
+    if (flavour != DMX_ESTEP_FAST || (tj != 4 && tj != 8)) tj = 4;
+    p.gp = (int)round_up(G, tj);
+    int n_tiles = 0;
+    for (int pi = 0; pi < p.gp / TILE; ++pi) n_tiles += p.gp / tj - (pi * TILE) / tj;
     p.n_tiles = n_tiles;
     const int quads = p.gp / 4;
     const int pieces_per_row = (quads + QPT - 1) / QPT;
@@ -447,7 +460,7 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
     if (p.row_groups * flush_rows > max_chunk_rows) flush_rows = 8;
     DMX_REQUIRE(p.row_groups * flush_rows <= max_chunk_rows, "n_genotypes %d too large for the pair kernel's staging", G);
     p.flushes = 1;
-    const int want_flushes = env_int("DMX_FLUSHES", 1);
+    const int want_flushes = env_int("DMX_FLUSHES", 2);
     while (p.flushes < want_flushes && p.row_groups * flush_rows * (p.flushes + 1) <= max_chunk_rows &&
            2 * (size_t)p.row_groups * flush_rows * (p.flushes + 1) * p.ld_smem * sizeof(float) <= 96 * 1024)
         ++p.flushes;
@@ -456,7 +469,7 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
     const int threads = (int)round_up(compute_threads > stagers ? compute_threads : stagers, 32);
     DMX_REQUIRE(threads <= MAX_THREADS, "internal: CTA too large after adding staging threads");
     size_t smem = 2 * (size_t)chunk_rows * p.ld_smem * sizeof(float);
-    if (p.row_groups > 1) smem += (size_t)p.tiles_per_cta * TILE * TILE * sizeof(double);
+    if (p.row_groups > 1) smem += (size_t)p.tiles_per_cta * TILE * tj * sizeof(double);
     DMX_REQUIRE(smem <= 200 * 1024, "shared memory request too large");
     p.doublet_bonus = doublet_bonus(G, doublet_prior);
     p.prior = prior_logits;
@@ -468,13 +481,17 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
     if (env_int("DMX_VERBOSE", 0))
         fprintf(stderr,
                 "[dmx] pair E-step: G=%d tiles=%d ctas/barcode=%d tiles/cta=%d row_groups=%d threads=%d flush_rows=%d "
-                "flushes=%d chunk_rows=%lld smem=%zu flavour=%d\n",
+                "flushes=%d chunk_rows=%lld smem=%zu flavour=%d tj=%d\n",
                 G, n_tiles, p.ctas_per_barcode, p.tiles_per_cta, p.row_groups, threads, flush_rows, p.flushes,
-                (long long)chunk_rows, smem, flavour);
+                (long long)chunk_rows, smem, flavour, tj);
 
-    if (flavour == DMX_ESTEP_EXACT) return launch_variant<DMX_ESTEP_EXACT, 8>(p, (unsigned)grid, threads, smem, stream);
-    if (flush_rows == 16) return launch_variant<DMX_ESTEP_FAST, 16>(p, (unsigned)grid, threads, smem, stream);
-    return launch_variant<DMX_ESTEP_FAST, 8>(p, (unsigned)grid, threads, smem, stream);
+    if (flavour == DMX_ESTEP_EXACT) return launch_variant<DMX_ESTEP_EXACT, 8, 4>(p, (unsigned)grid, threads, smem, stream);
+    if (tj == 8) {
+        if (flush_rows == 16) return launch_variant<DMX_ESTEP_FAST, 16, 8>(p, (unsigned)grid, threads, smem, stream);
+        return launch_variant<DMX_ESTEP_FAST, 8, 8>(p, (unsigned)grid, threads, smem, stream);
+    }
+    if (flush_rows == 16) return launch_variant<DMX_ESTEP_FAST, 16, 4>(p, (unsigned)grid, threads, smem, stream);
+    return launch_variant<DMX_ESTEP_FAST, 8, 4>(p, (unsigned)grid, threads, smem, stream);
 }
 
 }  // namespace dmx

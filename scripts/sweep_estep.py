@@ -26,7 +26,7 @@ print(f'G={G} C={C} B={pack.n_barcodes} R={pack.n_rows} updates={pack.n_rows * C
 
 
 def run(env, reps=5):
-    for k in ('DMX_RG', 'DMX_FLUSHES', 'DMX_FLUSH_ROWS', 'DMX_MAX_THREADS', 'DMX_MIN_BLOCKS', 'DMX_INT_WIDEN'):
+    for k in ('DMX_RG', 'DMX_FLUSHES', 'DMX_FLUSH_ROWS', 'DMX_MAX_THREADS', 'DMX_MIN_BLOCKS', 'DMX_INT_WIDEN', 'DMX_TJ'):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in env.items()})
     buffers = {}
@@ -44,7 +44,7 @@ def run(env, reps=5):
 
 
 base = None
-grid = dict(DMX_MIN_BLOCKS=[2, 3], DMX_MAX_THREADS=[128, 256], DMX_FLUSH_ROWS=[8, 16], DMX_FLUSHES=[1, 2])
+grid = dict(DMX_TJ=[4, 8], DMX_MAX_THREADS=[128, 256], DMX_FLUSH_ROWS=[16], DMX_FLUSHES=[1, 2])
 for combo in itertools.product(*grid.values()):
     env = dict(zip(grid.keys(), combo), DMX_VERBOSE=0)
     try:
