@@ -203,3 +203,106 @@ class BamFile:
                 if (end if end is not None else read.reference_start + 1) <= start:
                     continue
             yield read
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# header / index access without inflating the whole file (used by the native counting path)
+# ---------------------------------------------------------------------------------------------------------------
+
+def read_bam_header(path):
+    """(reference names, reference lengths, BGZF virtual offset of the first alignment record)."""
+    blocks: List[bytes] = []       # inflated blocks read so far
+    starts: List[int] = []         # compressed file offset of each block
+    with open(path, 'rb') as f:
+        def more() -> bool:
+            coffset = f.tell()
+            head = f.read(12)
+            if len(head) < 12:
+                return False
+            xlen = struct.unpack_from('<H', head, 10)[0]
+            extra = f.read(xlen)
+            size, p = None, 0
+            while p + 4 <= xlen:
+                slen = struct.unpack_from('<H', extra, p + 2)[0]
+                if extra[p] == 66 and extra[p + 1] == 67:
+                    size = struct.unpack_from('<H', extra, p + 4)[0] + 1
+                p += 4 + slen
+            if size is None:
+                raise ValueError('not a BGZF stream')
+            payload = f.read(size - 12 - xlen)
+            blocks.append(zlib.decompress(payload[:-8], -15))
+            starts.append(coffset)
+            return True
+
+        def need(n: int) -> bytes:
+            while sum(len(b) for b in blocks) < n:
+                if not more():
+                    raise ValueError('truncated BAM header')
+            return b''.join(blocks)
+
+        data = need(12)
+        if data[:4] != b'BAM\x01':
+            raise ValueError(f'{path} is not a BAM file')
+        l_text = struct.unpack_from('<i', data, 4)[0]
+        data = need(12 + l_text)
+        n_ref = struct.unpack_from('<i', data, 8 + l_text)[0]
+        off = 12 + l_text
+        names, lengths = [], []
+        for _ in range(n_ref):
+            data = need(off + 4)
+            l_name = struct.unpack_from('<i', data, off)[0]
+            data = need(off + 8 + l_name)
+            names.append(data[off + 4:off + 4 + l_name - 1].decode())
+            lengths.append(struct.unpack_from('<i', data, off + 4 + l_name)[0])
+            off += 8 + l_name
+        # translate the uncompressed offset of the first record into a virtual offset
+        consumed = 0
+        for block, coffset in zip(blocks, starts):
+            if off < consumed + len(block) or (off == consumed + len(block) and block is blocks[-1]):
+                if off == consumed + len(block):  # record starts exactly at the next block
+                    more_ok = more()
+                    return names, lengths, ((starts[-1] << 16) if more_ok else (coffset << 16) | len(block))
+                return names, lengths, (coffset << 16) | (off - consumed)
+            consumed += len(block)
+        raise ValueError('could not locate the first alignment record')
+
+
+def read_bai(path):
+    """Per reference: dict(mapped, unmapped, begin_voffset, linear) from a .bai index (SAM spec section 5.2)."""
+    raw = Path(path).read_bytes()
+    if raw[:4] != b'BAI\x01':
+        raise ValueError(f'{path} is not a BAI index')
+    n_ref = struct.unpack_from('<i', raw, 4)[0]
+    off = 8
+    out = []
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from('<i', raw, off)[0]
+        off += 4
+        entry = dict(mapped=0, unmapped=0, begin_voffset=None, linear=None)
+        for _b in range(n_bin):
+            bin_id, n_chunk = struct.unpack_from('<Ii', raw, off)
+            off += 8
+            if bin_id == 37450 and n_chunk == 2:  # metadata pseudo-bin
+                beg, _end, mapped, unmapped = struct.unpack_from('<QQQQ', raw, off)
+                entry.update(mapped=int(mapped), unmapped=int(unmapped), begin_voffset=int(beg))
+            off += 16 * n_chunk
+        n_intv = struct.unpack_from('<i', raw, off)[0]
+        off += 4
+        entry['linear'] = np.frombuffer(raw, dtype='<u8', count=n_intv, offset=off).copy()
+        off += 8 * n_intv
+        out.append(entry)
+    return out
+
+
+def region_start_voffset(index_entry: dict, start: Optional[int]) -> Optional[int]:
+    """A virtual offset at or before the first read overlapping `start` (16 kb linear index), None if unknown."""
+    linear = index_entry['linear']
+    if start is not None and len(linear):
+        window = min(int(start) >> 14, len(linear) - 1)
+        nonzero = linear[:window + 1][linear[:window + 1] != 0]
+        if len(nonzero) and linear[window] != 0:
+            return int(linear[window])
+        later = linear[window:][linear[window:] != 0]
+        if len(later):
+            return int(min(later[0], nonzero[-1]) if len(nonzero) else later[0])
+    return index_entry['begin_voffset']

@@ -17,6 +17,9 @@ LIB_PATH = CSRC / 'libdemux_b200.so'
 SOURCES = ['api.cu', 'builder.cu', 'table.cu', 'estep.cu', 'estep_pairs.cu', 'mstep.cu']
 HEADERS = [CSRC / 'common.cuh', CSRC.parent.parent / 'include' / 'demux_b200.h']
 
+HOST_SRC = CSRC.parent / 'csrc_host' / 'bam_counter.cpp'
+HOST_LIB_PATH = CSRC.parent / 'csrc_host' / 'libdemux_io.so'
+
 NVCC_FLAGS = [
     '-std=c++17', '-O3', '-lineinfo',
     '-gencode', 'arch=compute_100a,code=sm_100a',
@@ -69,6 +72,23 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB_PATH
 
 
+def build_host(force: bool = False) -> Path:
+    """libdemux_io.so: the native input stage (g++, zlib; no CUDA)."""
+    header = CSRC.parent.parent / 'include' / 'demux_io.h'
+    if not force and HOST_LIB_PATH.exists() and \
+            HOST_LIB_PATH.stat().st_mtime >= max(HOST_SRC.stat().st_mtime, header.stat().st_mtime):
+        return HOST_LIB_PATH
+    cxx = os.environ.get('CXX') or shutil.which('g++') or shutil.which('c++')
+    if not cxx:
+        raise RuntimeError('no C++ compiler found: libdemux_io.so cannot be built')
+    cmd = [cxx, '-O3', '-std=c++17', '-shared', '-fPIC', '-o', str(HOST_LIB_PATH), str(HOST_SRC), '-lz']
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f'host build failed:\n{" ".join(cmd)}\n{res.stdout}')
+    return HOST_LIB_PATH
+
+
 if __name__ == '__main__':
     path = build(force='--force' in sys.argv, verbose='--verbose' in sys.argv)
     print(path)
+    print(build_host(force='--force' in sys.argv))

@@ -16,9 +16,9 @@ from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 
-from .bam import BamFile, BamRecord
+from .bam import BamFile, BamRecord, read_bai, read_bam_header, region_start_voffset
 from .barcodes import BarcodeHandler
-from .calls import CompressedSNPCalls
+from .calls import MOLECULE_DTYPE, SNP_CALL_DTYPE, CompressedSNPCalls
 
 SEGMENT_LENGTH = 1000  # snp_counter.py:231: groups are flushed once reads have moved this far past them
 
@@ -129,9 +129,119 @@ def collapse_molecule(reads: List[Tuple[object, float]], snps: SnpPositions, ski
     return p_group, calls
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# native path (csrc_host/bam_counter.cpp through the C ABI of include/demux_io.h)
+# ---------------------------------------------------------------------------------------------------------------
+
+_NATIVE_FILTERS = {}  # read-filter callback -> its parameters for the native loop
+
+
+def _register_native_filter(fn, **params):
+    _NATIVE_FILTERS[fn] = params
+
+
+_register_native_filter(parse_read, umi_tag='UB', nhits_tag='NH', score_tag='AS', score_diff_max=8,
+                        mapq_threshold=20, p_misaligned_default=0.01)
+_register_native_filter(parse_read_bd_rhapsody, umi_tag='MA', nhits_tag='', score_tag='AS', score_diff_max=8,
+                        mapq_threshold=20, p_misaligned_default=0.01)
+
+_io_lib = None
+
+
+def native_io():
+    """ctypes handle of libdemux_io.so, or None when it has not been built (the Python loop is used then)."""
+    global _io_lib
+    if _io_lib is None:
+        import ctypes as C
+        from .build import HOST_LIB_PATH
+        if not HOST_LIB_PATH.exists():
+            _io_lib = False
+        else:
+            lib = C.CDLL(str(HOST_LIB_PATH))
+            lib.dmxio_last_error.restype = C.c_char_p
+            lib.dmxio_count_region.restype = C.c_void_p
+            lib.dmxio_count_region.argtypes = [C.c_char_p, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_void_p,
+                                               C.c_int64, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_char_p,
+                                               C.c_int32, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32,
+                                               C.c_double]
+            for name in ('dmxio_n_molecules', 'dmxio_n_calls', 'dmxio_n_reads_seen'):
+                getattr(lib, name).restype = C.c_int64
+                getattr(lib, name).argtypes = [C.c_void_p]
+            lib.dmxio_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.dmxio_copy.restype = None
+            lib.dmxio_free.argtypes = [C.c_void_p]
+            lib.dmxio_free.restype = None
+            _io_lib = lib
+    return _io_lib or None
+
+
+_INFO_CACHE: Dict[str, dict] = {}
+
+
+def _bam_info(path) -> dict:
+    """Header (+ .bai index when present) of a BAM, without inflating the alignments."""
+    key = str(path)
+    if key not in _INFO_CACHE:
+        names, lengths, first = read_bam_header(key)
+        bai = None
+        for candidate in (key + '.bai', key[:-4] + '.bai' if key.endswith('.bam') else None):
+            if candidate and Path(candidate).exists():
+                bai = read_bai(candidate)
+                break
+        _INFO_CACHE[key] = dict(names=names, lengths=lengths, first_voffset=first, bai=bai)
+    return _INFO_CACHE[key]
+
+
+def _whitelist_blob(barcode_handler: BarcodeHandler):
+    """Whitelist keys as one byte blob + offsets + compressed ids (tuple keys (CB, RG) are joined with 0x1f)."""
+    keys, ids = [], []
+    for key, idx in barcode_handler.barcode2index.items():
+        if isinstance(key, tuple):
+            key = key[0] + '\x1f' + key[1]
+        if isinstance(key, str):  # filter_to_rg_value() leaves integer placeholders for foreign barcodes
+            keys.append(key.encode())
+            ids.append(idx)
+    offsets = np.zeros(len(keys) + 1, dtype=np.int64)
+    np.cumsum([len(k) for k in keys], out=offsets[1:])
+    return b''.join(keys), offsets, np.asarray(ids, dtype=np.int32)
+
+
+def _count_region_native(lib, path: str, chromosome: str, positions: np.ndarray, barcode_handler: BarcodeHandler,
+                         params: dict, start, stop) -> CompressedSNPCalls:
+    info = _bam_info(path)
+    ref_id = info['names'].index(chromosome)
+    voffset = info['first_voffset']
+    if info['bai'] is not None:
+        from_index = region_start_voffset(info['bai'][ref_id], start)
+        voffset = from_index if from_index is not None else voffset
+    positions = np.ascontiguousarray(positions, dtype=np.int64)
+    blob, offsets, ids = _whitelist_blob(barcode_handler)
+    handle = lib.dmxio_count_region(
+        str(path).encode(), ref_id, voffset, -1 if start is None else int(start), -1 if stop is None else int(stop),
+        positions.ctypes.data, len(positions), blob, offsets.ctypes.data, ids.ctypes.data, len(ids),
+        barcode_handler.tag.encode(), int(barcode_handler.use_rg), params['umi_tag'].encode(),
+        params['nhits_tag'].encode(), params['score_tag'].encode(), params['score_diff_max'],
+        params['mapq_threshold'], params['p_misaligned_default'])
+    if not handle:
+        raise RuntimeError(f'native count_snps failed: {lib.dmxio_last_error().decode()}')
+    try:
+        out = CompressedSNPCalls.__new__(CompressedSNPCalls)
+        out.n_molecules, out.n_snp_calls = int(lib.dmxio_n_molecules(handle)), int(lib.dmxio_n_calls(handle))
+        out.molecules = np.empty(out.n_molecules, dtype=MOLECULE_DTYPE)
+        out.snp_calls = np.empty(out.n_snp_calls, dtype=SNP_CALL_DTYPE)
+        lib.dmxio_copy(handle, out.molecules.ctypes.data, out.snp_calls.ctypes.data)
+    finally:
+        lib.dmxio_free(handle)
+    return out
+
+
 def count_region(bamfile, chromosome: str, positions: np.ndarray, barcode_handler: BarcodeHandler,
-                 parse_read: Callable, start=None, stop=None) -> Tuple[str, CompressedSNPCalls]:
-    """One counting task (snp_counter.py:234-276)."""
+                 parse_read: Callable, start=None, stop=None, use_native: bool = True) -> Tuple[str, CompressedSNPCalls]:
+    """One counting task (snp_counter.py:234-276): native loop for the built-in read filters, Python otherwise."""
+    lib = native_io() if use_native else None
+    if lib is not None and parse_read in _NATIVE_FILTERS and not isinstance(bamfile, BamFile):
+        return chromosome, _count_region_native(lib, str(bamfile), chromosome, positions, barcode_handler,
+                                                _NATIVE_FILTERS[parse_read], start, stop)
     bam = bamfile if isinstance(bamfile, BamFile) else _open_cached(bamfile)
     snps = SnpPositions(positions)
     out = CompressedSNPCalls()
@@ -194,11 +304,14 @@ def plan_tasks(bamfile_location, chromosome2positions: Dict[str, np.ndarray], ba
             tasks.extend(plan_tasks(bamfile_location[rg], chromosome2positions, barcode_handler.filter_to_rg_value(rg),
                                     n_reads_per_job, minimum_fragment_length_per_job, minimum_overlap))
         return tasks
-    bam = _open_cached(bamfile_location)
-    mapped = bam.mapped_reads_per_reference()
+    info = _bam_info(bamfile_location)
+    if info['bai'] is not None:  # what pysam's get_index_statistics() reads
+        mapped = {name: entry['mapped'] for name, entry in zip(info['names'], info['bai'])}
+    else:
+        mapped = _open_cached(bamfile_location).mapped_reads_per_reference()
     ranked = []
     for chromosome, positions in chromosome2positions.items():
-        length = bam.get_reference_length(chromosome)
+        length = info['lengths'][info['names'].index(chromosome)]
         n_jobs = max(1, min(mapped[chromosome] // n_reads_per_job, length // minimum_fragment_length_per_job))
         cuts = np.searchsorted(positions, np.linspace(0, length, n_jobs + 1)[1:-1])
         for subset in np.split(positions, cuts):
@@ -212,17 +325,21 @@ def plan_tasks(bamfile_location, chromosome2positions: Dict[str, np.ndarray], ba
 
 
 def count_snps(bamfile_location, chromosome2positions: Dict[str, np.ndarray], barcode_handler: BarcodeHandler,
-               joblib_n_jobs=-1, joblib_verbosity=11, parse_read=parse_read) -> Dict[str, CompressedSNPCalls]:
+               joblib_n_jobs=-1, joblib_verbosity=11, parse_read=parse_read,
+               use_native: bool = True) -> Dict[str, CompressedSNPCalls]:
     """
     Which molecules carry information about which SNPs: {chromosome: CompressedSNPCalls}, the input of
     `Demultiplexer.predict_posteriors / learn_genotypes`.  Arguments as in the reference (snp_counter.py:279-302);
-    `bamfile_location` may be a path or, with an RG-aware barcode handler, a dict RG -> path.
+    `bamfile_location` may be a path or, with an RG-aware barcode handler, a dict RG -> path.  With the built-in
+    read filters (`parse_read`, `parse_read_bd_rhapsody`) the per-read loop runs in native code (libdemux_io.so)
+    with identical output; any other callback, or `use_native=False`, takes the Python loop.
     """
     tasks = plan_tasks(bamfile_location, chromosome2positions, barcode_handler)
 
     def run(task):
         bamfile, chromosome, start, stop, positions, handler = task
-        return count_region(bamfile, chromosome, positions, handler, parse_read, start=start, stop=stop)
+        return count_region(bamfile, chromosome, positions, handler, parse_read, start=start, stop=stop,
+                            use_native=use_native)
 
     if joblib_n_jobs == 1 or len(tasks) <= 1:
         results = [run(task) for task in tasks]
@@ -230,7 +347,7 @@ def count_snps(bamfile_location, chromosome2positions: Dict[str, np.ndarray], ba
         import joblib
         with joblib.Parallel(n_jobs=joblib_n_jobs, verbose=joblib_verbosity, pre_dispatch='all') as parallel:
             results = parallel(joblib.delayed(count_region)(bamfile, chromosome, positions, handler, parse_read,
-                                                            start=start, stop=stop)
+                                                            start=start, stop=stop, use_native=use_native)
                                for bamfile, chromosome, start, stop, positions, handler in tasks)
     per_chromosome = defaultdict(list)
     for chromosome, calls in results:

@@ -101,7 +101,26 @@ def test_collapse_molecule_rules():
     assert 30 not in got                                                         # two equally bad candidates: no call
 
 
-def test_count_snps_on_synthetic_bam(tmp_path):
+@pytest.fixture(scope='module', autouse=True)
+def _host_library():
+    from demuxalot_b200 import build
+    build.build_host()
+
+
+def test_native_library_exports_every_declared_symbol():
+    import re
+    from demuxalot_b200.counting import native_io
+    header = (Path(__file__).resolve().parent.parent / 'include' / 'demux_io.h').read_text()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(dmxio_[a-z0-9_]+)\s*\(', header))
+    lib = native_io()
+    assert lib is not None and declared
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+@pytest.mark.parametrize('use_native', [True, False], ids=['native', 'python'])
+def test_count_snps_on_synthetic_bam(tmp_path, use_native):
     genotypes = ProbabilisticGenotypes(['D1', 'D2'])
     for pos, bases in ((102, 'AC'), (107, 'CT'), (2100, 'GT'), (3004, 'AC')):
         for b in bases:
@@ -124,7 +143,8 @@ def test_count_snps_on_synthetic_bam(tmp_path):
     ]
     path = tmp_path / 't.bam'
     write_bam(path, [('chr1', 5000)], reads)
-    calls = count_snps(str(path), genotypes.get_chromosome2positions(), handler, joblib_n_jobs=1)
+    calls = count_snps(str(path), genotypes.get_chromosome2positions(), handler, joblib_n_jobs=1,
+                       use_native=use_native)
     assert list(calls) == ['chr1']
     c = calls['chr1']
     assert c.n_molecules == 3 and c.n_snp_calls == 5
@@ -142,8 +162,60 @@ def test_count_snps_on_synthetic_bam(tmp_path):
     assert np.array_equal(sc['p_base_wrong'], np.float32([1 * q30 * q20, q30, q30, q30, q30]))
 
 
+def test_native_and_python_loops_agree_on_a_random_bam(tmp_path):
+    """Randomised reads (soft clips, insertions, deletions, skips, duplicates, filtered reads, several barcodes and
+    UMIs, two references) through both implementations: identical records."""
+    rng = np.random.default_rng(11)
+    barcodes = [f'BC{k:03d}-1' for k in range(12)]
+    umis = [''.join(rng.choice(list('ACGT'), size=8)) for _ in range(40)]
+    reads = []
+    for ref_id in (0, 1):
+        pos = 0
+        for _ in range(1500):
+            pos += int(rng.integers(0, 9))
+            ops, length = [], 0
+            if rng.random() < 0.2:
+                ops.append(('S', int(rng.integers(1, 5))))
+            ops.append(('M', int(rng.integers(8, 30))))
+            extra = rng.random()
+            if extra < 0.15:
+                ops += [('I', int(rng.integers(1, 4))), ('M', int(rng.integers(5, 20)))]
+            elif extra < 0.3:
+                ops += [('D', int(rng.integers(1, 6))), ('M', int(rng.integers(5, 20)))]
+            elif extra < 0.45:
+                ops += [('N', int(rng.integers(50, 1500))), ('M', int(rng.integers(5, 20)))]
+            if rng.random() < 0.1:
+                ops.append(('H', 3))
+            n_query = sum(l for op, l in ops if op in 'MIS=X')
+            seq = ''.join(rng.choice(list('ACGTN'), size=n_query, p=[.24, .24, .24, .24, .04]))
+            qual = rng.integers(2, 42, size=n_query).tolist()
+            tags = {'NH': int(rng.choice([1, 1, 1, 2])), 'AS': int(n_query - rng.integers(0, 12)),
+                    'CB': str(rng.choice(barcodes + ['ZZZ-1']))}
+            if rng.random() < 0.95:
+                tags['UB'] = str(rng.choice(umis))
+            reads.append(encode_read(ref_id, pos, ops, seq, qual, mapq=int(rng.choice([255, 255, 3])), tags=tags))
+            if rng.random() < 0.1:
+                reads.append(reads[-1])  # complete duplicate
+    path = tmp_path / 'r.bam'
+    write_bam(path, [('chrA', 40000), ('chrB', 40000)], reads, block_bytes=1500)
+    positions = {c: np.unique(rng.integers(0, 9000, size=700)) for c in ('chrA', 'chrB')}
+    handler = BarcodeHandler(barcodes)
+    native = count_snps(str(path), positions, handler, joblib_n_jobs=1, use_native=True)
+    python = count_snps(str(path), positions, handler, joblib_n_jobs=1, use_native=False)
+    assert list(native) == list(python)
+    total = 0
+    for chrom in python:
+        a, b = native[chrom], python[chrom]
+        assert (a.n_molecules, a.n_snp_calls) == (b.n_molecules, b.n_snp_calls)
+        assert np.array_equal(a.molecules[:a.n_molecules], b.molecules[:b.n_molecules])
+        assert np.array_equal(a.snp_calls[:a.n_snp_calls], b.snp_calls[:b.n_snp_calls])
+        total += a.n_snp_calls
+    assert total > 500
+
+
 @pytest.mark.skipif(not reference_available(), reason='/root/reference not mounted')
-def test_example_bam_matches_reference_fixture():
+@pytest.mark.parametrize('use_native', [True, False], ids=['native', 'python'])
+def test_example_bam_matches_reference_fixture(use_native):
     """Our reader + counting on the bundled example reproduce the reference's calls exactly (first 48 barcodes are
     stored in the committed fixture; sizes of the full run in example_data_summary.json)."""
     import json
@@ -152,7 +224,8 @@ def test_example_bam_matches_reference_fixture():
     genotypes = ProbabilisticGenotypes(['Donor01', 'Donor02', 'Donor03', 'Donor04'])
     genotypes.add_vcf(EXAMPLE / 'test_genotypes.vcf')
     handler = BarcodeHandler.from_file(EXAMPLE / 'test_barcodes.csv')
-    calls = count_snps(str(EXAMPLE / 'test_bamfile.bam'), genotypes.get_chromosome2positions(), handler, joblib_n_jobs=1)
+    calls = count_snps(str(EXAMPLE / 'test_bamfile.bam'), genotypes.get_chromosome2positions(), handler, joblib_n_jobs=1,
+                       use_native=use_native)
     summary = json.loads((GOLDEN_DIR / 'example_data_summary.json').read_text())
     assert list(calls) == list(summary['chromosomes'])  # same task order -> same dict order
     for chrom, sizes in summary['chromosomes'].items():
