@@ -32,7 +32,7 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
 // ---------------------------------------------------------------------------------------------------------------
 
 // Each lane owns 4 consecutive genotypes (one 128-bit load of a table row), a row needs LPR lanes, a warp works on
-// 32 / LPR rows at once with eight rows in flight; row records of 32 rows are read with one coalesced load per
+// 32 / LPR rows at once with four such waves in flight; row records of 32 rows are read with one coalesced load per
 // array and handed around with shuffles.
 template <int FLAVOUR, int LPR, int SLOTS>
 __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __restrict__ offsets,
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __re
                                                              int64_t ld_prior, float* __restrict__ logits,
                                                              int64_t ld_logits) {
     constexpr int RGW = 32 / LPR;                  // rows a warp processes at once
-    constexpr int WAVES = 8 / RGW > 0 ? 8 / RGW : 1;
+    constexpr int WAVES = 4;                       // row waves in flight (measured: more costs occupancy)
     constexpr int PASSES_PER_FLUSH = FLUSH_ROWS / WAVES > 0 ? FLUSH_ROWS / WAVES : 1;
     __shared__ double partial[4][SLOTS * 4][32];
     const int lane = threadIdx.x & 31;

@@ -5,7 +5,7 @@
 // Rows come in the reference's own order (CSC: ascending variant, then barcode).  One warp per variant.  A warp
 // reads the row records of 32 rows with one coalesced load per array and walks them with shuffles.  Each lane owns
 // 4 consecutive genotypes (one 128-bit load of the singlet-posterior row, which is L2 resident: B x G x 4 bytes),
-// so a row needs LPR = G/4 lanes and a warp works on 32/LPR rows at once, eight rows in flight.  Every lane adds its
+// so a row needs LPR = G/4 lanes and a warp works on 32/LPR rows at once, four such waves in flight.  Every lane adds its
 // rows in ascending order in float64; the 32/LPR row groups are then combined in a fixed order, i.e. the result is
 // deterministic and equals the reference's sequential float64 sum up to float64 re-association (a difference is
 // only visible if the exact sum lies within 1e-16 relative of a float32 rounding boundary).  Variants with more
@@ -18,12 +18,12 @@ namespace dmx {
 
 constexpr int MSTEP_WARPS = 8;
 constexpr int HEAVY_ROWS = 4096;
-constexpr int IN_FLIGHT = 8;  // rows whose gathers are issued before any is consumed
+constexpr int WAVES_IN_FLIGHT = 4;  // row waves whose gathers are issued before any is consumed (measured: 2-4 best)
 
 template <int LPR, int SLOTS, bool SQUARE, bool FULL>
 struct RowWalker {
     static constexpr int RGW = 32 / LPR;        // row groups per warp
-    static constexpr int WAVES = IN_FLIGHT / RGW > 0 ? IN_FLIGHT / RGW : 1;
+    static constexpr int WAVES = WAVES_IN_FLIGHT;
     double acc[SLOTS][4];
     int lane, sub, rgw;
 
@@ -53,10 +53,11 @@ struct RowWalker {
                 const int32_t cb = __shfl_sync(0xffffffffu, my_cb, k & 31);
                 w[u] = __shfl_sync(0xffffffffu, my_w, k & 31);
                 const float4* row = reinterpret_cast<const float4*>(post + (int64_t)cb * ld_post);
+                const bool wave_has_rows = k0 + u * RGW < n;  // warp-uniform: whole waves past the end are skipped
 #pragma unroll
                 for (int s = 0; s < SLOTS; ++s) {
                     const int q = sub + LPR * s;
-                    x[u][s] = (FULL || q < n_quads) ? __ldg(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    x[u][s] = (wave_has_rows && (FULL || q < n_quads)) ? __ldg(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
 #pragma unroll
