@@ -125,7 +125,11 @@ class Demultiplexer:
     device: Optional[torch.device] = None  # None -> current CUDA device
     process_group = None  # torch.distributed group for barcode-sharded / multi-lane EM (see distributed.py)
     schedule_barcodes = True  # launch the deepest barcodes first (dmx_barcode_schedule)
-    mstep_allreduce_tiles = 4  # variant-range tiles: all-reduce of tile k overlaps the M-step of tile k + 1
+    # variant-range tiles of the sharded M-step: all-reduce of tile k overlaps the M-step of tile k + 1.  Measured
+    # (profiles/r01_allreduce_sweep_*.json): the 168 MB all-reduce is 0.34 ms over NVLink, every extra tile costs
+    # ~0.25 ms of stream hand-over, so one tile wins; more tiles only pay off for tables of many GB.
+    mstep_allreduce_tiles = 1
+    mstep_allreduce_dtype = 'float64'  # 'float64': rounded once after the global sum; 'float32': half the bytes
 
     # ------------------------------------------------------------------------------------------------ helpers
     @classmethod
@@ -360,15 +364,16 @@ class Demultiplexer:
         sharded = cls.process_group is not None
         if out is None:
             out = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float32, device=dev)
-        if sharded and out64 is None:
+        wide = sharded and cls.mstep_allreduce_dtype == 'float64'
+        if wide and out64 is None:
             out64 = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             def launch(v_lo: int, v_hi: int) -> None:
                 _native.check(lib.dmx_mstep(
                     pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
                     singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, float(cls.contribution_power),
-                    0 if sharded else out.data_ptr(), pack.n_genotypes, _native.ptr(out64), pack.n_genotypes,
-                    v_lo, v_hi, _stream()), 'dmx_mstep')
+                    0 if wide else out.data_ptr(), pack.n_genotypes, _native.ptr(out64) if wide else 0,
+                    pack.n_genotypes, v_lo, v_hi, _stream()), 'dmx_mstep')
 
             if not sharded:
                 launch(0, pack.n_variants)
@@ -376,18 +381,23 @@ class Demultiplexer:
             # (f) of north_star: the partial variant x genotype sums of all barcode shards are combined with one
             # sum all-reduce per EM iteration.  The variant range is cut into tiles: NCCL reduces tile k (on its
             # own stream, async_op) while the M-step kernel computes tile k + 1.  Partials travel as float64 so
-            # the single rounding to float32 happens after the global sum, exactly as on one GPU.
+            # the single rounding to float32 happens after the global sum, exactly as on one GPU
+            # (mstep_allreduce_dtype = 'float32' halves the bytes on the wire at the price of one extra float32
+            # rounding per shard: about world_size ulp on the addition, far inside the parity tolerance).
             import torch.distributed as dist
+            partial = out64 if wide else out
             n_tiles = max(1, min(cls.mstep_allreduce_tiles, pack.n_variants))
             bounds = [pack.n_variants * k // n_tiles for k in range(n_tiles + 1)]
             pending = []
             for v_lo, v_hi in zip(bounds[:-1], bounds[1:]):
                 if v_hi > v_lo:
                     launch(v_lo, v_hi)
-                    pending.append(dist.all_reduce(out64[v_lo:v_hi], op=dist.ReduceOp.SUM,
+                    pending.append(dist.all_reduce(partial[v_lo:v_hi], op=dist.ReduceOp.SUM,
                                                    group=cls.process_group, async_op=True))
             for work in pending:
                 work.wait()
+            if not wide:
+                return out
             _native.check(lib.dmx_round_f64_to_f32(
                 out64.data_ptr(), pack.n_genotypes, out.data_ptr(), pack.n_genotypes, pack.n_variants,
                 pack.n_genotypes, _stream()), 'dmx_round_f64_to_f32')

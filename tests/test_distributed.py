@@ -131,6 +131,14 @@ def _nccl_worker(rank: int, world: int, port: int, out_dir: str) -> None:
             lane_learnt, _ = Demultiplexer.learn_genotypes(lane.calls, lane.genotypes, lane.barcode_handler,
                                                            n_iterations=3, doublet_prior=0.35)
         np.save(os.path.join(out_dir, f'lane_betas_{rank}.npy'), np.array(lane_learnt.get_betas()))
+        # float32 partial sums on the wire: one extra rounding per shard, otherwise the same protocol
+        Demultiplexer.mstep_allreduce_dtype, Demultiplexer.mstep_allreduce_tiles = 'float32', 3
+        try:
+            narrow, _ = learn_genotypes_sharded(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4,
+                                                doublet_prior=0.35)
+        finally:
+            Demultiplexer.mstep_allreduce_dtype, Demultiplexer.mstep_allreduce_tiles = 'float64', 1
+        np.save(os.path.join(out_dir, f'betas_f32_{rank}.npy'), np.array(narrow.get_betas()))
     finally:
         dist.destroy_process_group()
 
@@ -148,3 +156,5 @@ def test_two_gpu_sharded_em_matches_single_gpu(tmp_path, native_lib):
     p0, p1, ps = (np.load(tmp_path / f) for f in ('post_0.npy', 'post_1.npy', 'post_single.npy'))
     assert np.array_equal(p0, p1) and np.abs(p0 - ps).max() <= 1e-6
     assert np.array_equal(np.load(tmp_path / 'lane_betas_0.npy'), np.load(tmp_path / 'lane_betas_1.npy'))
+    n0, n1 = np.load(tmp_path / 'betas_f32_0.npy'), np.load(tmp_path / 'betas_f32_1.npy')
+    assert np.array_equal(n0, n1) and np.allclose(n0, bs, rtol=2e-6, atol=1e-7)
