@@ -27,18 +27,21 @@ SIGNATURES = {
     'dmx_prior_betas': (C.c_int, [_ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _ptr, _f64, _ptr, _ptr, _i64, _ptr]),
     'dmx_probs_from_betas': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr, _ptr, _i64, _f32, _f32, _ptr,
                                        _i64, _ptr]),
-    'dmx_estep_workspace_bytes': (_i64, [_i64, _i32, _f64]),
+    'dmx_estep_workspace_bytes': (_i64, [_i64, _i32, _f64, _i64, _i32]),
+    'dmx_estep_plan_supported': (C.c_int, [_i32, _f64, _i32]),
+    'dmx_estep_plan_workspace_bytes': (_i64, [_i64]),
+    'dmx_estep_plan': (C.c_int, [_ptr, _ptr, _i64, _i32, _ptr, _ptr, _i64, _ptr, _i64, C.POINTER(_i64), _ptr]),
     'dmx_barcode_schedule_workspace_bytes': (_i64, [_i64]),
     'dmx_barcode_schedule': (C.c_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr]),
     'dmx_estep': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
-                            _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr]),
+                            _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _ptr, _i64, _i32, _ptr]),
     'dmx_softmax_rows': (C.c_int, [_ptr, _i64, _i64, _i32, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     'dmx_mstep': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
     'dmx_round_f64_to_f32': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr]),
 }
 
 ESTEP_EXACT, ESTEP_FAST = 0, 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class NativeError(RuntimeError):

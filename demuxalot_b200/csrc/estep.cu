@@ -13,6 +13,8 @@
 //          [1e-4, 1.0001], so a product stays a normal number), one lg2.approx per product, float64 accumulation.
 #include <math_constants.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 
 namespace dmx {
@@ -26,6 +28,19 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
                        double doublet_prior,
                        float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
                        int64_t ld_logits, int flavour, cudaStream_t stream);
+
+// estep_pairs_warp.cu
+bool estep_pairs_warp_supported(int G, int flavour);
+int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* seg_prefix,
+                            const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
+                            const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
+                            float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
+                            int64_t ld_logits, double* partial, int64_t n_cols, cudaStream_t stream);
+float pair_doublet_bonus(int n_genotypes, double dp);
+int launch_plan_segments(const int64_t* offsets, const int32_t* order, int64_t n_barcodes, int seg_rows,
+                         int32_t* n_seg, cudaStream_t stream);
+int launch_plan_items(const int32_t* seg_prefix, int64_t n_barcodes, int64_t capacity, int32_t* item_slot,
+                      cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------------------------
 // singlets only (doublet_prior == 0): one CTA of 4 warps per barcode, lanes over genotypes
@@ -145,14 +160,44 @@ __global__ void __launch_bounds__(128) estep_singlets_kernel(const int64_t* __re
 // row softmax: one CTA per barcode
 // ---------------------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) softmax_rows_kernel(const float* __restrict__ logits, int64_t ld_logits,
-                                                           int n_cols, float* __restrict__ post, int64_t ld_post,
+// Segment sums of the warp pair kernel (estep_pairs_warp.cu): a barcode cut into several work items has its float64
+// log2-sums added here in segment order, then penalty, prior logits and the single rounding to float32.
+struct CombineParams {
+    const int32_t* order;       // schedule slot -> barcode (or nullptr); blockIdx.x is a slot when seg_prefix is set
+    const int32_t* seg_prefix;  // nullptr: no combine stage, blockIdx.x is the barcode
+    const double* partial;
+    const double* prior;
+    int64_t ld_prior;
+    int n_singlets;
+    float doublet_bonus;
+};
+
+__global__ void __launch_bounds__(128) softmax_rows_kernel(float* __restrict__ logits, int64_t ld_logits, int n_cols,
+                                                           float* __restrict__ post, int64_t ld_post,
                                                            float* __restrict__ singlets, int64_t ld_singlet,
-                                                           int n_singlets) {
+                                                           int n_singlets, const CombineParams cp) {
     __shared__ float s_max[4];
     __shared__ double s_sum[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float* row = logits + (int64_t)blockIdx.x * ld_logits;
+    int64_t barcode = blockIdx.x;
+    if (cp.seg_prefix) {
+        const int seg_first = cp.seg_prefix[blockIdx.x];
+        const int n_seg = cp.seg_prefix[blockIdx.x + 1] - seg_first;
+        if (cp.order) barcode = cp.order[blockIdx.x];
+        if (n_seg > 1) {  // every thread later re-reads only the columns it writes here
+            float* out = logits + barcode * ld_logits;
+            for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
+                double sum = 0.0;
+                for (int k = 0; k < n_seg; ++k) sum += cp.partial[(int64_t)(seg_first + k) * n_cols + c];
+                const float pen = c < cp.n_singlets ? 0.f : cp.doublet_bonus;
+                float logit = (float)((double)pen + sum * 0.693147180559945309417232);
+                if (cp.prior) logit = (float)((double)logit + cp.prior[barcode * cp.ld_prior + c]);
+                out[c] = logit;
+            }
+        }
+        if (!post && !singlets) return;
+    }
+    const float* row = logits + barcode * ld_logits;
 
     float m = -CUDART_INF_F;
     for (int c = threadIdx.x; c < n_cols; c += blockDim.x) m = fmaxf(m, row[c]);
@@ -170,17 +215,20 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(const float* __restri
 
     for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
         const float pr = __fdiv_rn(expf(__fsub_rn(row[c], m)), total);
-        if (post) post[(int64_t)blockIdx.x * ld_post + c] = pr;
-        if (singlets && c < n_singlets) singlets[(int64_t)blockIdx.x * ld_singlet + c] = pr;
+        if (post) post[barcode * ld_post + c] = pr;
+        if (singlets && c < n_singlets) singlets[barcode * ld_singlet + c] = pr;
     }
 }
 
-static int launch_softmax(const float* logits, int64_t ld_logits, int64_t n_rows, int n_cols, float* post,
-                          int64_t ld_post, float* singlets, int64_t ld_singlet, int n_singlets, cudaStream_t stream) {
+static int launch_softmax(float* logits, int64_t ld_logits, int64_t n_rows, int n_cols, float* post,
+                          int64_t ld_post, float* singlets, int64_t ld_singlet, int n_singlets, cudaStream_t stream,
+                          const CombineParams* combine = nullptr) {
     if (n_rows <= 0 || n_cols <= 0) return 0;
-    if (!post && !singlets) return 0;
+    CombineParams cp = {};
+    if (combine) cp = *combine;
+    if (!post && !singlets && !cp.seg_prefix) return 0;
     softmax_rows_kernel<<<(unsigned)n_rows, 128, 0, stream>>>(logits, ld_logits, n_cols, post, ld_post, singlets,
-                                                              ld_singlet, n_singlets);
+                                                              ld_singlet, n_singlets, cp);
     DMX_LAUNCH_CHECK();
     return 0;
 }
@@ -211,16 +259,60 @@ static int launch_singlets(unsigned grid, cudaStream_t stream, const int64_t* of
 
 extern "C" {
 
-int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior) {
-    const int64_t cols = doublet_prior == 0 ? n_genotypes : (int64_t)n_genotypes * (n_genotypes + 1) / 2;
+static int64_t logits_scratch_bytes(int64_t n_barcodes, int64_t cols) {
     return dmx::round_up(n_barcodes * cols * (int64_t)sizeof(float), 256) + 256;
+}
+
+int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior, int64_t n_items,
+                                  int32_t need_logits_scratch) {
+    const int64_t cols = doublet_prior == 0 ? n_genotypes : (int64_t)n_genotypes * (n_genotypes + 1) / 2;
+    int64_t bytes = need_logits_scratch ? logits_scratch_bytes(n_barcodes, cols) : 0;
+    if (n_items > n_barcodes) bytes += dmx::round_up(n_items * cols * (int64_t)sizeof(double), 256);
+    return bytes;
 }
 
 int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int32_t n_cols, float* posteriors,
                      int64_t ld_post, float* singlet_posteriors, int64_t ld_singlet, int32_t n_singlets,
                      void* stream) {
-    return dmx::launch_softmax(logits, ld_logits, n_rows, n_cols, posteriors, ld_post, singlet_posteriors, ld_singlet,
-                               n_singlets, (cudaStream_t)stream);
+    return dmx::launch_softmax(const_cast<float*>(logits), ld_logits, n_rows, n_cols, posteriors, ld_post,
+                               singlet_posteriors, ld_singlet, n_singlets, (cudaStream_t)stream);
+}
+
+int dmx_estep_plan_supported(int32_t n_genotypes, double doublet_prior, int32_t flavour) {
+    return doublet_prior != 0 && dmx::estep_pairs_warp_supported(n_genotypes, flavour) ? 1 : 0;
+}
+
+int64_t dmx_estep_plan_workspace_bytes(int64_t n_barcodes) {
+    size_t temp = 0;
+    const int64_t m = n_barcodes + 1;
+    if (cub::DeviceScan::ExclusiveSum(nullptr, temp, (const int32_t*)nullptr, (int32_t*)nullptr, m) != cudaSuccess)
+        return -1;
+    return dmx::round_up((int64_t)temp, 256) + dmx::round_up(4 * m, 256);
+}
+
+int dmx_estep_plan(const int64_t* barcode_offsets, const int32_t* barcode_order, int64_t n_barcodes, int32_t seg_rows,
+                   int32_t* seg_prefix, int32_t* item_slot, int64_t item_capacity, void* workspace,
+                   int64_t workspace_bytes, int64_t* h_n_items, void* stream_) {
+    using namespace dmx;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (h_n_items) *h_n_items = 0;
+    if (n_barcodes <= 0) return 0;
+    DMX_REQUIRE(seg_rows >= 16 && seg_rows <= 4096, "seg_rows %d outside [16, 4096]", seg_rows);
+    DMX_REQUIRE(workspace_bytes >= dmx_estep_plan_workspace_bytes(n_barcodes), "plan workspace too small");
+    const int64_t m = n_barcodes + 1;
+    int32_t* n_seg = (int32_t*)workspace;
+    void* temp = (uint8_t*)workspace + round_up(4 * m, 256);
+    size_t temp_bytes = (size_t)(workspace_bytes - round_up(4 * m, 256));
+    if (launch_plan_segments(barcode_offsets, barcode_order, n_barcodes, seg_rows, n_seg, stream)) return -1;
+    DMX_CUDA(cub::DeviceScan::ExclusiveSum(temp, temp_bytes, (const int32_t*)n_seg, seg_prefix, m, stream));
+    if (launch_plan_items(seg_prefix, n_barcodes, item_capacity, item_slot, stream)) return -1;
+    int32_t n_items = 0;
+    DMX_CUDA(cudaMemcpyAsync(&n_items, seg_prefix + n_barcodes, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    DMX_CUDA(cudaStreamSynchronize(stream));
+    DMX_REQUIRE(n_items <= item_capacity, "item_slot too small: %d items, capacity %lld", n_items,
+                (long long)item_capacity);
+    if (h_n_items) *h_n_items = n_items;
+    return 0;
 }
 
 int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* csr_variant,
@@ -228,7 +320,8 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
               const float* table, int64_t ld_table, int32_t n_genotypes, double doublet_prior,
               const double* prior_logits, int64_t ld_prior, float* logits, int64_t ld_logits, float* posteriors,
               int64_t ld_post, float* singlet_posteriors, int64_t ld_singlet, void* workspace,
-              int64_t workspace_bytes, int32_t flavour, float table_floor, void* stream_) {
+              int64_t workspace_bytes, int32_t flavour, float table_floor, const int32_t* seg_prefix,
+              const int32_t* item_slot, int64_t n_items, int32_t seg_rows, void* stream_) {
     using namespace dmx;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_barcodes <= 0) return 0;
@@ -241,13 +334,24 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
     const int64_t n_cols = doublet_prior == 0 ? G : (int64_t)G * (G + 1) / 2;
     DMX_REQUIRE(n_cols < (1ll << 31), "too many columns");
 
+    const bool planned = seg_prefix && item_slot && n_items > 0 && doublet_prior != 0 &&
+                         estep_pairs_warp_supported(G, flavour);
+    uint8_t* ws = (uint8_t*)workspace;
+    int64_t ws_left = workspace ? workspace_bytes : 0;
     float* out_logits = logits;
     int64_t ld_out = ld_logits;
     if (!out_logits) {
-        DMX_REQUIRE(workspace && workspace_bytes >= n_barcodes * n_cols * (int64_t)sizeof(float),
-                    "workspace too small for the logits scratch");
-        out_logits = (float*)workspace;
+        const int64_t need = logits_scratch_bytes(n_barcodes, n_cols);
+        DMX_REQUIRE(ws_left >= need, "workspace too small for the logits scratch");
+        out_logits = (float*)ws;
         ld_out = n_cols;
+        ws += need;
+        ws_left -= need;
+    }
+    double* partial = nullptr;
+    if (planned && n_items > n_barcodes) {
+        DMX_REQUIRE(ws_left >= n_items * n_cols * (int64_t)sizeof(double), "workspace too small for the segment sums");
+        partial = (double*)ws;
     }
 
     if (doublet_prior == 0) {
@@ -259,6 +363,23 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
             rc = launch_singlets<DMX_ESTEP_EXACT>((unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
                                                   csr_e, table, ld_table, G, prior_logits, ld_prior, out_logits, ld_out);
         if (rc) return rc;
+    } else if (planned) {
+        const int rc = launch_estep_pairs_warp(barcode_offsets, barcode_order, seg_prefix, item_slot, n_items, seg_rows,
+                                               csr_variant, csr_e, table, ld_table, G, doublet_prior, table_floor,
+                                               prior_logits, ld_prior, out_logits, ld_out, partial, n_cols, stream);
+        if (rc) return rc;
+        if (partial) {
+            CombineParams cp;
+            cp.order = barcode_order;
+            cp.seg_prefix = seg_prefix;
+            cp.partial = partial;
+            cp.prior = prior_logits;
+            cp.ld_prior = ld_prior;
+            cp.n_singlets = G;
+            cp.doublet_bonus = pair_doublet_bonus(G, doublet_prior);
+            return launch_softmax(out_logits, ld_out, n_barcodes, (int)n_cols, posteriors, ld_post, singlet_posteriors,
+                                  ld_singlet, G, stream, &cp);
+        }
     } else {
         const int rc = launch_estep_pairs(barcode_offsets, barcode_order, csr_variant, csr_e, n_barcodes, table, ld_table, G,
                                           doublet_prior, table_floor, prior_logits, ld_prior, out_logits, ld_out,

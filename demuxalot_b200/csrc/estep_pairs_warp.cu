@@ -1,0 +1,441 @@
+// Pair E-step, warp-autonomous flavour (FAST arithmetic, 17 <= G <= 56): one warp = one work item.
+//
+//   S_b[i, j] = sum_{rows r of barcode b} log( 0.5 (P[v_r, i] + P[v_r, j]) (1 - e_r) + max(e_r, 1e-4) ),  i <= j
+//
+// Same arithmetic as the FAST flavour of estep_pairs.cu (running float32 products of x = a_i + a_j, a =
+// fma(P, 1 - e, e'); the binary exponents are moved into integer sums every FLUSH_ROWS rows; one lg2 per pair at
+// the end), different decomposition:
+//   * a work item is a barcode, or a segment of at most ~seg_rows rows of a deep barcode (dmx_estep_plan); items
+//     are launched deepest barcode first, one 32-thread CTA each, so there is no CTA-wide barrier anywhere: a warp
+//     stages its own table rows (cp.async, double buffered) and only ever executes __syncwarp;
+//   * the upper triangle of the pair matrix is cut into 8 x 8 register tiles (64 running products per lane, 32
+//     independent FADD2 -> FMUL2 chains): four LDS.128 feed 64 updates, half the shared-memory wavefronts per
+//     update of the 4 x 4 tiles, which were co-limiting with the packed-FP32 pipe;
+//   * lanes = RG row groups x T tiles (G = 32: 3 x 10); the row groups are reduced with shuffles in a fixed order;
+//   * the exponent sums of two packed products share one register (2 x 16 bits): a lane flushes at most
+//     seg_rows / FLUSH_ROWS + 1 times and a flushed product is < 2^17, so 16 bits cannot overflow for
+//     seg_rows <= 4096 (checked by the launcher);
+//   * segments of a multi-segment barcode write float64 log2-sums to a scratch matrix; the softmax kernel adds
+//     them in segment order (deterministic) and produces the float32 logits.
+#include "common.cuh"
+
+namespace dmx {
+
+constexpr float WARP_ERROR_FLOOR = 1e-4f;
+
+struct WarpPairsParams {
+    const int64_t* offsets;     // barcode_offsets [B + 1]
+    const int32_t* order;       // schedule slot -> barcode, or nullptr (identity)
+    const int32_t* seg_prefix;  // [B + 1] by schedule slot: first item of the slot
+    const int32_t* item_slot;   // [n_items]
+    const int32_t* variant;
+    const float* e;
+    const float* table;
+    int64_t ld_table;
+    int n_genotypes;
+    float doublet_bonus;
+    const double* prior;
+    int64_t ld_prior;
+    float* logits;
+    int64_t ld_logits;
+    double* partial;  // [n_items, n_cols] log2-sums, written by the segments of multi-segment barcodes only
+    int64_t n_cols;
+};
+
+__device__ __forceinline__ uint64_t wpack2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void wunpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t wadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t wmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float wlg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int NB>
+struct WarpShape {
+    static constexpr int GP = 8 * NB;               // genotypes padded to the tile width
+    static constexpr int T = NB * (NB + 1) / 2;     // 8 x 8 tiles of the upper triangle (diagonal included)
+    static constexpr int RG = 32 / T;               // row groups in the warp
+    static constexpr int LD = GP + 4;               // floats per staged row (bank-conflict-free row stride)
+    static constexpr int QUADS = GP / 4;            // 16-byte pieces per row
+    static constexpr int QPS = NB;                  // quads per staging slot: half a row
+};
+
+template <int NB, int FLUSH_ROWS, bool ESUM16, int MIN_WARPS, int UNROLL>
+__global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const WarpPairsParams p) {
+    using S = WarpShape<NB>;
+    constexpr int T = S::T, RG = S::RG, LD = S::LD, QPS = S::QPS;
+    constexpr int CHUNK = RG * FLUSH_ROWS;          // rows per staged chunk = one flush per lane
+    constexpr int SPL = (2 * CHUNK + 31) / 32;      // staging slots per lane and chunk
+    constexpr int DUMP_LD = 33;                     // epilogue dump: words per lane and array (+1: no bank conflicts)
+    constexpr int STAGE_FLOATS = 2 * CHUNK * LD;
+    constexpr int SMEM_FLOATS = STAGE_FLOATS > 3 * 32 * DUMP_LD ? STAGE_FLOATS : 3 * 32 * DUMP_LD;
+    __shared__ __align__(16) float smem[SMEM_FLOATS];
+    float* const stage0 = smem;
+    float* const stage1 = smem + CHUNK * LD;
+
+    const int lane = threadIdx.x;
+    const int item = blockIdx.x;
+    const int slot = __ldg(p.item_slot + item);
+    const int seg_first = __ldg(p.seg_prefix + slot);
+    const int n_seg = __ldg(p.seg_prefix + slot + 1) - seg_first;
+    const int seg = item - seg_first;
+    const int64_t barcode = p.order ? (int64_t)__ldg(p.order + slot) : (int64_t)slot;
+    const int64_t b_lo = __ldg(p.offsets + barcode), b_hi = __ldg(p.offsets + barcode + 1);
+    // segments: equal length, a multiple of CHUNK, so only the last one carries padding rows
+    const int64_t per = ((b_hi - b_lo + n_seg - 1) / n_seg + CHUNK - 1) / CHUNK * CHUNK;
+    int64_t row_lo = b_lo + (int64_t)seg * per;
+    if (row_lo > b_hi) row_lo = b_hi;
+    const int64_t row_hi = row_lo + per < b_hi ? row_lo + per : b_hi;
+    const int n_chunks = (int)((row_hi - row_lo + CHUNK - 1) / CHUNK);
+
+    // lane -> (row group, tile); lanes beyond RG * T shadow the last row group (they only stage and shuffle)
+    int rg = lane / T;
+    const int tile = lane - rg * T;
+    const bool has_tile = rg < RG;
+    if (!has_tile) rg = RG - 1;
+    int ti = 0, tj = tile;  // tile -> (I, J), I <= J, I-major
+    while (tj >= NB - ti) { tj -= NB - ti; ++ti; }
+    tj += ti;
+
+    uint64_t prod[4][8];                       // running products: [i pair][j], mantissas kept in [1, 2)
+    unsigned esum[ESUM16 ? 4 : 8][8];          // biased exponents moved out of the products
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) prod[a][b] = wpack2(1.f, 1.f);
+#pragma unroll
+    for (int a = 0; a < (ESUM16 ? 4 : 8); ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) esum[a][b] = 0u;
+
+    // ---- staging: slot k of a lane = half (lane & 1) of chunk row (lane >> 1) + 16 k -----------------------------
+    const int piece = lane & 1;
+    const int n_table_quads = (int)(p.ld_table / 4);
+    int v_pre[SPL];
+    float e_pre[SPL], e_cur[SPL];
+    unsigned live = 0;
+
+    auto prefetch = [&](int chunk) {
+        const int64_t base = row_lo + (int64_t)chunk * CHUNK + (lane >> 1);
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int64_t row = base + 16 * k;
+            v_pre[k] = -1;
+            e_pre[k] = 0.f;
+            if ((lane >> 1) + 16 * k < CHUNK && row < row_hi) {
+                v_pre[k] = __ldg(p.variant + row);
+                e_pre[k] = __ldg(p.e + row);
+            }
+        }
+    };
+    auto issue = [&](float* buf) {
+        live = 0;
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            const int r = (lane >> 1) + 16 * k;
+            if (r < CHUNK) {
+                float* dst = buf + r * LD + 4 * QPS * piece;
+                e_cur[k] = e_pre[k];
+                if (v_pre[k] >= 0) {
+                    const float* src = p.table + (int64_t)v_pre[k] * p.ld_table + 4 * QPS * piece;
+                    live |= 1u << k;
+#pragma unroll
+                    for (int u = 0; u < QPS; ++u) {
+                        if (QPS * piece + u < n_table_quads) cp_async_16(dst + 4 * u, src + 4 * u);
+                        else *reinterpret_cast<float4*>(dst + 4 * u) = make_float4(1.f, 1.f, 1.f, 1.f);
+                    }
+                } else {  // padding row: a = 1 -> factor 2 -> log2 = 1, removed in the epilogue
+#pragma unroll
+                    for (int u = 0; u < QPS; ++u) *reinterpret_cast<float4*>(dst + 4 * u) = make_float4(1.f, 1.f, 1.f, 1.f);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    auto land = [&](float* buf) {  // every lane finishes the pieces it copied itself
+        cp_async_wait<0>();
+#pragma unroll
+        for (int k = 0; k < SPL; ++k) {
+            if (live & (1u << k)) {
+                float* dst = buf + ((lane >> 1) + 16 * k) * LD + 4 * QPS * piece;
+                const float e = e_cur[k];
+                const float w = __fsub_rn(1.f, e);
+                const float ef = fmaxf(e, WARP_ERROR_FLOOR);
+#pragma unroll
+                for (int u = 0; u < QPS; ++u) {
+                    if (QPS * piece + u < n_table_quads) {
+                        float4 x = *reinterpret_cast<float4*>(dst + 4 * u);
+                        x.x = fmaf(x.x, w, ef);
+                        x.y = fmaf(x.y, w, ef);
+                        x.z = fmaf(x.z, w, ef);
+                        x.w = fmaf(x.w, w, ef);
+                        *reinterpret_cast<float4*>(dst + 4 * u) = x;
+                    }
+                }
+            }
+        }
+    };
+
+    if (n_chunks > 0) {
+        prefetch(0);
+        issue(stage0);
+        if (n_chunks > 1) prefetch(1);
+        land(stage0);
+        __syncwarp();
+    }
+
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        float* cur = (chunk & 1) ? stage1 : stage0;
+        float* nxt = (chunk & 1) ? stage0 : stage1;
+        const bool more = chunk + 1 < n_chunks;
+        if (more) {
+            issue(nxt);
+            if (chunk + 2 < n_chunks) prefetch(chunk + 2);
+        }
+
+        // The row loop is deliberately NOT fully unrolled: 16 rows x 64 packed instructions are 25 KB of code per
+        // chunk and every warp of the SM sits at a different place in it, which made instruction fetch the top
+        // stall (ncu: no_instruction, 81 % i-cache hit rate).  UNROLL rows per iteration fit the L0 i-cache; the
+        // operands of the next row are loaded before the current one is consumed (register double buffer).
+        const float* rows = cur + rg * LD;
+        float4 i_lo = *reinterpret_cast<const float4*>(rows + 8 * ti);
+        float4 i_hi = *reinterpret_cast<const float4*>(rows + 8 * ti + 4);
+        float4 j_lo = *reinterpret_cast<const float4*>(rows + 8 * tj);
+        float4 j_hi = *reinterpret_cast<const float4*>(rows + 8 * tj + 4);
+#pragma unroll UNROLL
+        for (int k = 0; k < FLUSH_ROWS; ++k) {
+            const float* s = rows + (k + 1 < FLUSH_ROWS ? k + 1 : k) * (RG * LD);
+            const float4 n_i_lo = *reinterpret_cast<const float4*>(s + 8 * ti);
+            const float4 n_i_hi = *reinterpret_cast<const float4*>(s + 8 * ti + 4);
+            const float4 n_j_lo = *reinterpret_cast<const float4*>(s + 8 * tj);
+            const float4 n_j_hi = *reinterpret_cast<const float4*>(s + 8 * tj + 4);
+            const uint64_t ai[4] = {wpack2(i_lo.x, i_lo.y), wpack2(i_lo.z, i_lo.w), wpack2(i_hi.x, i_hi.y),
+                                    wpack2(i_hi.z, i_hi.w)};
+            const float aj[8] = {j_lo.x, j_lo.y, j_lo.z, j_lo.w, j_hi.x, j_hi.y, j_hi.z, j_hi.w};
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const uint64_t bj = wpack2(aj[b], aj[b]);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) prod[a][b] = wmul2(prod[a][b], wadd2(ai[a], bj));
+            }
+            i_lo = n_i_lo; i_hi = n_i_hi; j_lo = n_j_lo; j_hi = n_j_hi;
+        }
+        // renormalise: exponents into the integer sums, mantissas back to [1, 2) (exact)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                float lo, hi;
+                wunpack2(prod[a][b], lo, hi);
+                const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
+                if constexpr (ESUM16) {
+                    esum[a][b] += (blo >> 23) + ((bhi & 0x7f800000u) >> 7);
+                } else {
+                    esum[2 * a][b] += blo >> 23;
+                    esum[2 * a + 1][b] += bhi >> 23;
+                }
+                prod[a][b] = wpack2(__uint_as_float((blo & 0x007fffffu) | 0x3f800000u),
+                                    __uint_as_float((bhi & 0x007fffffu) | 0x3f800000u));
+            }
+
+        if (more) land(nxt);
+        __syncwarp();
+    }
+
+    // ---- epilogue -------------------------------------------------------------------------------------------------
+    // Every lane dumps its 64 (exponent sum, log2 mantissa) results into the now idle staging memory; then the warp
+    // walks the barcode's pairs as a rolled, lane-parallel loop: fixed-order sum over the row groups (deterministic),
+    // penalty, prior, one rounding to float32.  Runs of 8 consecutive columns are written together.
+    unsigned* dump_e = reinterpret_cast<unsigned*>(smem);
+    float* dump_lo = smem + 32 * DUMP_LD;
+    float* dump_hi = smem + 2 * 32 * DUMP_LD;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            float lo, hi;
+            wunpack2(prod[a][b], lo, hi);
+            unsigned packed;
+            if constexpr (ESUM16) packed = esum[a][b];
+            else packed = (esum[2 * a][b] & 0xffffu) | (esum[2 * a + 1][b] << 16);
+            dump_e[lane * DUMP_LD + a * 8 + b] = packed;
+            dump_lo[lane * DUMP_LD + a * 8 + b] = wlg2(lo);
+            dump_hi[lane * DUMP_LD + a * 8 + b] = wlg2(hi);
+        }
+    __syncwarp();
+
+    const int G = p.n_genotypes;
+    const int bias = 127 * n_chunks;
+    const double padded_rows = (double)n_chunks * (double)CHUNK;
+#pragma unroll 1
+    for (int idx = lane; idx < T * 64; idx += 32) {
+        const int t = idx >> 6, q = idx & 63;
+        const int a = q >> 4, h = (q >> 3) & 1, b = q & 7;
+        int oi = 0, oj = t;
+        while (oj >= NB - oi) { oj -= NB - oi; ++oi; }
+        oj += oi;
+        const int i = 8 * oi + 2 * a + h, j = 8 * oj + b;
+        if (i < G && j < G && j >= i) {
+            double sum = 0.0;
+#pragma unroll
+            for (int g = 0; g < RG; ++g) {
+                const int src = (g * T + t) * DUMP_LD + a * 8 + b;
+                const unsigned e2 = dump_e[src];
+                const int ev = (int)(h ? e2 >> 16 : e2 & 0xffffu) - bias;
+                sum += (double)ev + (double)(h ? dump_hi[src] : dump_lo[src]);
+            }
+            sum -= padded_rows;
+            const int64_t col = (i == j) ? i : (int64_t)G + (int64_t)i * G - (int64_t)i * (i + 1) / 2 + (j - i - 1);
+            if (n_seg == 1) {
+                const float pen = (i == j) ? 0.f : p.doublet_bonus;
+                float logit = (float)((double)pen + sum * 0.693147180559945309417232);
+                if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
+                p.logits[barcode * p.ld_logits + col] = logit;
+            } else {
+                p.partial[(int64_t)item * p.n_cols + col] = sum;
+            }
+        }
+    }
+}
+
+// ---- work items ---------------------------------------------------------------------------------------------------
+
+__global__ void plan_segments_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ order,
+                                     int64_t n_barcodes, int seg_rows, int32_t* __restrict__ n_seg) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s <= n_barcodes;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        int32_t n = 0;
+        if (s < n_barcodes) {
+            const int64_t b = order ? (int64_t)order[s] : s;
+            const int64_t rows = offsets[b + 1] - offsets[b];
+            n = (int32_t)(rows <= seg_rows ? 1 : (rows + seg_rows - 1) / seg_rows);
+        }
+        n_seg[s] = n;
+    }
+}
+
+__global__ void plan_items_kernel(const int32_t* __restrict__ seg_prefix, int64_t n_barcodes, int64_t capacity,
+                                  int32_t* __restrict__ item_slot) {
+    for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < n_barcodes;
+         s += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lo = seg_prefix[s], hi = seg_prefix[s + 1];
+        for (int64_t k = lo; k < hi && k < capacity; ++k) item_slot[k] = (int32_t)s;
+    }
+}
+
+static inline int plan_grid(int64_t n, int threads) {
+    int64_t blocks = ceil_div(n > 0 ? n : 1, threads);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+int launch_plan_segments(const int64_t* offsets, const int32_t* order, int64_t n_barcodes, int seg_rows,
+                         int32_t* n_seg, cudaStream_t stream) {
+    plan_segments_kernel<<<plan_grid(n_barcodes + 1, 256), 256, 0, stream>>>(offsets, order, n_barcodes, seg_rows, n_seg);
+    DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_plan_items(const int32_t* seg_prefix, int64_t n_barcodes, int64_t capacity, int32_t* item_slot,
+                      cudaStream_t stream) {
+    plan_items_kernel<<<plan_grid(n_barcodes, 256), 256, 0, stream>>>(seg_prefix, n_barcodes, capacity, item_slot);
+    DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+float pair_doublet_bonus(int n_genotypes, double dp) {  // demux.py:168-172
+    const double g = (double)n_genotypes;
+    double bonus = log(g * dp);
+    bonus -= log(g * (double)(n_genotypes - 1 > 1 ? n_genotypes - 1 : 1) / 2 * (1 - dp));
+    return (float)bonus;
+}
+
+static int warp_env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
+
+bool estep_pairs_warp_supported(int G, int flavour) {
+    if (flavour != DMX_ESTEP_FAST) return false;
+    if (warp_env_int("DMX_PAIRS_WARP", 1) == 0) return false;
+    const int nb = (G + 7) / 8;
+    return nb == 3 || nb == 4 || nb == 5 || nb == 7;  // lane utilisation >= 28 / 32; other widths: estep_pairs.cu
+}
+
+template <int NB, int FLUSH_ROWS, bool ESUM16, int MIN_WARPS, int UNROLL>
+static int launch_warp_variant(const WarpPairsParams& p, int64_t n_items, cudaStream_t stream) {
+    auto kernel = estep_pairs_warp_kernel<NB, FLUSH_ROWS, ESUM16, MIN_WARPS, UNROLL>;
+    DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+    kernel<<<(unsigned)n_items, 32, 0, stream>>>(p);
+    DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* seg_prefix,
+                            const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
+                            const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
+                            float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
+                            int64_t ld_logits, double* partial, int64_t n_cols, cudaStream_t stream) {
+    DMX_REQUIRE(seg_rows >= 16 && seg_rows <= 4096, "seg_rows %d outside [16, 4096]", seg_rows);
+    DMX_REQUIRE(n_items > 0 && n_items < (1ll << 31), "bad item count %lld", (long long)n_items);
+    WarpPairsParams p;
+    p.offsets = barcode_offsets;
+    p.order = barcode_order;
+    p.seg_prefix = seg_prefix;
+    p.item_slot = item_slot;
+    p.variant = csr_variant;
+    p.e = csr_e;
+    p.table = table;
+    p.ld_table = ld_table;
+    p.n_genotypes = G;
+    p.doublet_bonus = pair_doublet_bonus(G, doublet_prior);
+    p.prior = prior_logits;
+    p.ld_prior = ld_prior;
+    p.logits = logits;
+    p.ld_logits = ld_logits;
+    p.partial = partial;
+    p.n_cols = n_cols;
+    // 16 factors per product need 16 * -log2(2 (floor + 1e-4)) <= 120 binades; 8 factors are always safe
+    const bool long_products = table_floor >= 0.0027f && warp_env_int("DMX_FLUSH_ROWS", 16) == 16;
+    const int nb = (G + 7) / 8;
+    const int variant = warp_env_int("DMX_WARP_VARIANT", 0);  // experiments: exponent packing / occupancy target
+#define DMX_WARP(NB_, E16_, MINW_, UNROLL_)                                                         \
+    return long_products ? launch_warp_variant<NB_, 16, E16_, MINW_, UNROLL_>(p, n_items, stream)   \
+                         : launch_warp_variant<NB_, 8, E16_, MINW_, UNROLL_>(p, n_items, stream)
+    switch (nb) {
+        case 3: DMX_WARP(3, true, 12, 2);
+        case 4:
+            if (variant == 1) { DMX_WARP(4, true, 12, 1); }
+            if (variant == 2) { DMX_WARP(4, true, 12, 4); }
+            if (variant == 3) { DMX_WARP(4, true, 12, 8); }
+            if (variant == 4) { DMX_WARP(4, true, 10, 2); }
+            if (variant == 5) { DMX_WARP(4, true, 14, 2); }
+            if (variant == 6) { DMX_WARP(4, true, 16, 2); }
+            DMX_WARP(4, true, 12, 2);
+        case 5: DMX_WARP(5, true, 12, 2);
+        case 7: DMX_WARP(7, true, 12, 2);
+        default: break;
+    }
+#undef DMX_WARP
+    set_error("warp pair kernel does not support %d genotypes", G);
+    return -2;
+}
+
+}  // namespace dmx

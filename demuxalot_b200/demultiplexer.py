@@ -125,6 +125,9 @@ class Demultiplexer:
     device: Optional[torch.device] = None  # None -> current CUDA device
     process_group = None  # torch.distributed group for barcode-sharded / multi-lane EM (see distributed.py)
     schedule_barcodes = True  # launch the deepest barcodes first (dmx_barcode_schedule)
+    # warp-per-item pair E-step (dmx_estep_plan): barcodes deeper than this many rows are cut into segments
+    # (16..4096); 0 disables the plan and every width runs on the CTA-per-barcode kernel
+    estep_segment_rows = 4096
     # variant-range tiles of the sharded M-step: all-reduce of tile k overlaps the M-step of tile k + 1.  Measured
     # (profiles/r01_allreduce_sweep_*.json): the 168 MB all-reduce is 0.34 ms over NVLink, every extra tile costs
     # ~0.25 ms of stream hand-over, so one tile wins; more tiles only pay off for tables of many GB.
@@ -313,6 +316,33 @@ class Demultiplexer:
         return out
 
     @classmethod
+    def _estep_plan(cls, pack: DevicePack, doublet_prior: float):
+        """Work items of the warp pair kernel for this pack: (seg_prefix, item_slot, n_items, seg_rows) or None.
+        Computed once per pack and schedule setting (the plan only depends on the barcode depths)."""
+        lib = _native.load()
+        seg_rows = int(cls.estep_segment_rows)
+        if seg_rows <= 0 or pack.n_barcodes == 0 or \
+                not lib.dmx_estep_plan_supported(pack.n_genotypes, float(doublet_prior), cls._flavour()):
+            return None
+        cache = pack.__dict__.setdefault('_estep_plans', {})
+        key = (seg_rows, bool(cls.schedule_barcodes))
+        if key not in cache:
+            dev = pack.device
+            capacity = pack.n_barcodes + pack.n_rows // seg_rows + 1
+            seg_prefix = torch.empty(pack.n_barcodes + 1, dtype=torch.int32, device=dev)
+            item_slot = torch.empty(capacity, dtype=torch.int32, device=dev)
+            ws_bytes = lib.dmx_estep_plan_workspace_bytes(pack.n_barcodes)
+            ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            h_items = C.c_int64(0)
+            with torch.cuda.device(dev):
+                _native.check(lib.dmx_estep_plan(
+                    pack.barcode_offsets.data_ptr(), pack.barcode_order.data_ptr() if cls.schedule_barcodes else 0,
+                    pack.n_barcodes, seg_rows, seg_prefix.data_ptr(), item_slot.data_ptr(), capacity, ws.data_ptr(),
+                    ws_bytes, C.byref(h_items), _stream()), 'dmx_estep_plan')
+            cache[key] = (seg_prefix, item_slot, int(h_items.value), seg_rows)
+        return cache[key]
+
+    @classmethod
     def _e_step(cls, pack: DevicePack, table: torch.Tensor, doublet_prior: float,
                 prior_logits: Optional[torch.Tensor] = None, want_logits: bool = True, want_post: bool = True,
                 want_singlets: bool = False, buffers: Optional[dict] = None):
@@ -337,9 +367,12 @@ class Demultiplexer:
             singlets = buffers.get('singlets')
             if singlets is None or tuple(singlets.shape) != shape:
                 singlets = buffers['singlets'] = torch.zeros(shape, dtype=torch.float32, device=dev)
-        workspace, ws_bytes = None, 0
-        if logits is None:
-            ws_bytes = lib.dmx_estep_workspace_bytes(pack.n_barcodes, pack.n_genotypes, float(doublet_prior))
+        plan = cls._estep_plan(pack, doublet_prior)
+        seg_prefix, item_slot, n_items, seg_rows = plan if plan is not None else (None, None, 0, 0)
+        workspace = None
+        ws_bytes = lib.dmx_estep_workspace_bytes(pack.n_barcodes, pack.n_genotypes, float(doublet_prior), n_items,
+                                                 1 if logits is None else 0)
+        if ws_bytes > 0:
             workspace = buffers.get('estep_ws')
             if workspace is None or workspace.numel() < ws_bytes:
                 workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -352,6 +385,7 @@ class Demultiplexer:
                 _native.ptr(logits), n_cols, _native.ptr(post), n_cols, _native.ptr(singlets),
                 cls._table_ld(pack.n_genotypes),
                 _native.ptr(workspace), ws_bytes, cls._flavour(), float(getattr(table, 'dmx_floor', 0.0)),
+                _native.ptr(seg_prefix), _native.ptr(item_slot), n_items, seg_rows,
                 _stream()), 'dmx_estep')
         return logits, post, singlets
 

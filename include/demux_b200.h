@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DMX_ABI_VERSION 1
+#define DMX_ABI_VERSION 2
 
 /* E-step arithmetic flavours (see DESIGN.md "E-step") */
 #define DMX_ESTEP_EXACT 0 /* per-term float32 argument roundings + logf of demux.py:261, float64 accumulation */
@@ -111,18 +111,36 @@ int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addi
  * Outputs (each may be NULL): logits [B, ld_logits], posteriors [B, ld_post], singlet posteriors
  * [B, ld_singlet] (first G columns of the softmax; the only part the M-step reads, demux.py:115).
  * `table` is the output of dmx_probs_from_betas with ld_table a multiple of 4.
- * scratch: float32 [n_barcodes * C] when `logits` is NULL (workspace query below), else unused.
+ * workspace (query below): float32 [n_barcodes * C] when `logits` is NULL, plus float64 [n_items * C] partial sums
+ * when a plan with multi-segment barcodes (n_items > n_barcodes) is given.
  * `table_floor`: a lower bound of the table entries (the clip_lo given to dmx_probs_from_betas), or 0 if
  * unknown; the FAST flavour uses it to decide how many row factors it may multiply before taking one log.
  */
-int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior);
+int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior, int64_t n_items,
+                                  int32_t need_logits_scratch);
 int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order /* dmx_barcode_schedule, or NULL */,
               const int32_t* csr_variant, const float* csr_e, int64_t n_barcodes,
               const float* table, int64_t ld_table, int32_t n_genotypes,
               double doublet_prior, const double* prior_logits, int64_t ld_prior,
               float* logits, int64_t ld_logits, float* posteriors, int64_t ld_post,
               float* singlet_posteriors, int64_t ld_singlet,
-              void* workspace, int64_t workspace_bytes, int32_t flavour, float table_floor, void* stream);
+              void* workspace, int64_t workspace_bytes, int32_t flavour, float table_floor,
+              const int32_t* seg_prefix, const int32_t* item_slot, int64_t n_items, int32_t seg_rows /* dmx_estep_plan,
+              or NULL, NULL, 0, 0 */, void* stream);
+
+/* Work items of the warp-per-item pair E-step (FAST flavour, doublet_prior != 0, see dmx_estep_plan_supported): a
+ * barcode with more than seg_rows rows is cut into ceil(rows / seg_rows) segments so that no single warp carries a
+ * deep barcode alone; the segments' float64 partial sums are added in segment order (deterministic).  Outputs, by
+ * schedule slot s (barcode = barcode_order[s], or s when barcode_order is NULL): seg_prefix int32 [n_barcodes + 1]
+ * (first item of slot s; seg_prefix[n_barcodes] = number of items) and item_slot int32 [item_capacity]
+ * (item -> slot); item_capacity >= n_barcodes + n_rows / seg_rows always suffices.  No reference counterpart; the
+ * results do not depend on the plan beyond float64 regrouping.  Synchronises `stream` once to return *h_n_items.
+ * workspace: dmx_estep_plan_workspace_bytes(n_barcodes). */
+int dmx_estep_plan_supported(int32_t n_genotypes, double doublet_prior, int32_t flavour);
+int64_t dmx_estep_plan_workspace_bytes(int64_t n_barcodes);
+int dmx_estep_plan(const int64_t* barcode_offsets, const int32_t* barcode_order, int64_t n_barcodes, int32_t seg_rows,
+                   int32_t* seg_prefix, int32_t* item_slot, int64_t item_capacity, void* workspace,
+                   int64_t workspace_bytes, int64_t* h_n_items, void* stream);
 
 /* row softmax only (scipy.special.softmax(x, axis=-1), demux.py:101,152); outputs as in dmx_estep */
 int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int32_t n_cols,

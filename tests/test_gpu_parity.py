@@ -242,6 +242,60 @@ def test_shapes_vs_oracle(D, shape, flavour):
     assert rel.max() <= 1e-5
 
 
+# widths served by the warp-per-item pair kernel (8 x 8 register tiles: 3, 4, 5 and 7 blocks of 8 genotypes), with
+# segment lengths that cut most barcodes into several work items, against the oracle and against the CTA kernel
+WARP_SHAPES = [
+    dict(n_genotypes=17, n_snps=500, n_barcodes=60, rows_per_barcode=150, seed=31),
+    dict(n_genotypes=24, n_snps=900, n_barcodes=50, rows_per_barcode=260, seed=32, empty_barcode_fraction=0.2),
+    dict(n_genotypes=30, n_snps=2500, n_barcodes=120, rows_per_barcode=700, seed=33, shuffle_variants=True),
+    dict(n_genotypes=37, n_snps=1200, n_barcodes=40, rows_per_barcode=180, seed=34),
+    dict(n_genotypes=53, n_snps=1500, n_barcodes=30, rows_per_barcode=120, seed=35),
+]
+
+
+@pytest.mark.parametrize('seg_rows', [4096, 64, 16])
+@pytest.mark.parametrize('shape', WARP_SHAPES, ids=lambda s: f"G{s['n_genotypes']}")
+def test_warp_pair_kernel_widths_and_segments(D, native_lib, shape, seg_rows):
+    from demuxalot_b200.synthetic import make_dataset
+    import torch
+    ds = make_dataset(**shape)
+    G = shape['n_genotypes']
+    D.estep_flavour = 'fast'
+    assert native_lib.dmx_estep_plan_supported(G, 0.35, 1) == 1
+    O = oracle.OracleDemultiplexer
+    ol, op = O.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.35)
+    old = D.estep_segment_rows
+    try:
+        D.estep_segment_rows = seg_rows
+        gl, gp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.35)
+        check_logits_and_posteriors(f'warp/G{G}/seg{seg_rows}', gl.values, ol.values, gp.values, op.values)
+        # the plan itself: every barcode appears in ceil(rows / seg_rows) consecutive items (at least one)
+        pack = D._pack_device(ds.calls, ds.genotypes, ds.barcode_handler.n_barcodes, add_data_prior=False)
+        seg_prefix, item_slot, n_items, _ = D._estep_plan(pack, 0.35)
+        depth = np.diff(pack.barcode_offsets.cpu().numpy())[pack.barcode_order.cpu().numpy()]
+        want_segments = np.maximum(1, -(-depth // seg_rows))
+        assert np.array_equal(np.diff(seg_prefix.cpu().numpy()), want_segments)
+        assert n_items == want_segments.sum()
+        assert np.array_equal(item_slot.cpu().numpy()[:n_items], np.repeat(np.arange(len(depth)), want_segments))
+        # prior logits go through the segment combine as well
+        prior = np.random.default_rng(5).normal(size=gl.shape) * 3
+        table = D._probs_table(pack, None, 0.01)
+        with_prior, _, _ = D._e_step(pack, table, 0.35, prior_logits=torch.from_numpy(prior).to(pack.device))
+        want = (gl.values.astype(np.float64) + prior).astype(np.float32)
+        assert np.array_equal(with_prior.cpu().numpy(), want)
+        # same numbers as the CTA-per-barcode kernel up to the regrouping of the float32 products
+        D.estep_segment_rows = 0
+        cl, cp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.35)
+        rel = np.abs(cl.values.astype(np.float64) - gl.values) / np.maximum(np.abs(cl.values), 1e-30)
+        assert rel.max() <= 2e-6
+    finally:
+        D.estep_segment_rows = old
+    gg, _ = D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4, doublet_prior=0.35)
+    og, _ = O.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4, doublet_prior=0.35)
+    ob, gb = np.array(og.get_betas(), np.float64), np.array(gg.get_betas(), np.float64)
+    assert (np.abs(gb - ob) / np.maximum(np.abs(ob), 1e-3)).max() <= 1e-5
+
+
 def test_no_calls_and_unknown_chromosome(D):
     from demuxalot_b200 import CompressedSNPCalls
     case = load_case('g4_dp25')

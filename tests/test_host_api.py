@@ -24,10 +24,16 @@ def test_abi_library_exports_every_declared_symbol(native_lib):
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     for name in declared:
         assert hasattr(native_lib, name), name
-    assert native_lib.dmx_abi_version() == 1
+    assert native_lib.dmx_abi_version() == _native.ABI_VERSION == 2
     # size queries are pure host functions: callable without a GPU
-    assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.25) >= 10 * 10 * 4
-    assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.0) >= 10 * 4 * 4
+    assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.25, 0, 1) >= 10 * 10 * 4
+    assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.0, 0, 1) >= 10 * 4 * 4
+    assert native_lib.dmx_estep_workspace_bytes(10, 32, 0.35, 10, 0) == 0  # one item per barcode: no segment sums
+    assert native_lib.dmx_estep_workspace_bytes(10, 32, 0.35, 14, 0) >= 14 * 528 * 8
+    # widths served by the warp-per-item pair kernel (FAST flavour, doublet columns)
+    assert [g for g in range(1, 70) if native_lib.dmx_estep_plan_supported(g, 0.35, 1)] == \
+        list(range(17, 41)) + list(range(49, 57))
+    assert not native_lib.dmx_estep_plan_supported(32, 0.0, 1) and not native_lib.dmx_estep_plan_supported(32, 0.35, 0)
 
 
 def test_product_path_fails_loudly_without_cuda():
