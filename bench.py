@@ -297,6 +297,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         Demultiplexer.process_group = None
 
         # end to end through the public API, host inputs (pinned) -> host DataFrames
+        # (the synthetic dataset holds millions of small Python objects -- var2varid keys, barcodes; a cyclic-GC pass
+        # over them costs 20-200 ms and used to land inside a timed call at random: freeze them out of the collector)
+        import gc
+        gc.collect()
+        gc.freeze()
         e2e_steps = args.e2e_steps or max(3, min(args.steps, 5))
         for _ in range(min(args.warmup, 2)):
             Demultiplexer.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=DOUBLET_PRIOR)
@@ -315,7 +320,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     value = units_per_step * args.steps / (total_ms / 1e3)
     e2e_s = reduce_max(sum(e2e_times)) / e2e_steps
     e2e_value = units_per_step / e2e_s
-    h2d = sum(13 * c.n_snp_calls + 12 * c.n_molecules for c in ds.calls.values()) + V * G * 4 + V * (8 + 4 + 4) + 4 * (pack.n_snps + 1)
+    # bytes that cross PCIe per call: packed snp_calls records, the compressed_cb column of the molecules (gathered by
+    # host threads into a pinned staging buffer; the full 12-byte records when host_gather_threads == 0) and the betas;
+    # the sorted genotype keys / SNP index are derived from the genotypes object and cached on the device with it
+    mol_bytes = 4 if Demultiplexer.host_gather_threads > 0 else 12
+    h2d = sum(13 * c.n_snp_calls + mol_bytes * c.n_molecules for c in ds.calls.values()) + V * G * 4
     d2h = 2 * B * C * 4
     em_total_ms = reduce_max(sum(em_ms))
 
@@ -351,22 +360,27 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         },
         'clocks': clocks,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-                'ms_per_step': 1e3 * e2e_s, 'steps': e2e_steps,
-                'api': 'Demultiplexer.predict_posteriors(host CompressedSNPCalls, genotypes, barcode_handler)'},
+                'ms_per_step': 1e3 * e2e_s, 'steps': e2e_steps, 'ms_each': [round(1e3 * t, 2) for t in e2e_times],
+                'api': 'Demultiplexer.predict_posteriors(host CompressedSNPCalls, genotypes, barcode_handler)',
+                'host_gather_threads': int(Demultiplexer.host_gather_threads), 'gc': 'dataset objects frozen (gc.freeze)'},
         'gpu_launches': 3 * args.steps,
-        'gpu_launches_note': 'per step: probs_table_kernel, estep_pairs_kernel, softmax_rows_kernel',
+        'gpu_launches_note': 'per step: probs_table_vec4_kernel, estep_pairs_warp_kernel, softmax_rows_kernel',
         'roofline': {
-            'kernel': 'estep_pairs_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+            'kernel': 'estep_pairs_warp_kernel', 'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_kind': peak_kind,
             'algorithmic_bytes_per_launch': int(algorithmic_bytes), 'kernel_ms': kernel_s * 1e3,
-            'note': 'the pair E-step is FP32-issue/MUFU bound, not HBM bound (0.26 B per update at G=32); see alu',
+            'note': 'the pair E-step is bound by the FP32 pipe, not by HBM (0.26 B per update at G=32); see alu',
             'alu': {
                 'updates_per_s': R * C / kernel_s,
                 'updates_per_clk_per_sm': R * C / kernel_s / (sm_count * sm_mhz * 1e6),
-                # measured on this GPU type with scripts/microbench_fp32x2.cu (profiles/r01_microbench.log): a
-                # dependent FADD2 -> FMUL2 pair stream issues 2.27 warp-instructions/clk/SM = 72.6 updates/clk/SM
-                'issue_ceiling_updates_per_clk_per_sm': 72.6,
-                'frac_of_issue_ceiling': R * C / kernel_s / (sm_count * sm_mhz * 1e6) / 72.6,
+                # measured on this GPU type with scripts/microbench_packed_tile.cu (profiles/r01_microbench_packed_tile.log):
+                # FADD2 / FMUL2 / FFMA2 issue at 2.0 warp-instructions/clk/SM in any mix (128 FP32 lane-ops/clk/SM, the
+                # same lanes as scalar FP32); one update = one add + one multiply -> 64 updates/clk/SM
+                'fp32_pipe_ceiling_updates_per_clk_per_sm': 64.0,
+                'frac_of_fp32_pipe_ceiling': R * C / kernel_s / (sm_count * sm_mhz * 1e6) / 64.0,
+                # 8 x 8 register tiles waste the lower halves of the diagonal tiles (528 of 640 slots useful at G=32)
+                # and 30 of 32 lanes carry tiles: 64 * 528/640 * 30/32
+                'tiling_ceiling_updates_per_clk_per_sm': 64.0 * (C / (64.0 * (((G + 7) // 8) * ((G + 7) // 8 + 1) // 2))) * (30 / 32 if (G + 7) // 8 == 4 else 1.0),
             },
         },
         'em': {'iterations_per_s': args.steps / (em_total_ms / 1e3), 'ms_per_iteration': em_total_ms / args.steps,

@@ -19,7 +19,8 @@ SIGNATURES = {
     'dmx_last_error': (C.c_char_p, []),
     'dmx_device_info': (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(_i64), C.POINTER(_i64)]),
-    'dmx_unpack_match_calls': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    'dmx_unpack_match_calls': (C.c_int, [_ptr, _i64, _ptr, _i64, _i32, _i64, _ptr, _ptr, _i64, _ptr, _ptr, _ptr, _ptr]),
+    'dmx_host_gather_cb': (C.c_int, [_ptr, _i64, _ptr, _i32]),
     'dmx_build_rows_workspace_bytes': (_i64, [_i64, _i64, _i64]),
     'dmx_build_rows': (C.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _i64,
                                  _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,

@@ -1,6 +1,11 @@
 // Boundary plumbing: ABI version, thread-local error text, device info, small utility kernels.
 #include <stdarg.h>
 
+#include <thread>
+#include <vector>
+
+#include <string.h>
+
 #include "common.cuh"
 
 namespace dmx {
@@ -41,6 +46,36 @@ int dmx_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int
     if (cc_minor) *cc_minor = prop.minor;
     if (l2_bytes) *l2_bytes = prop.l2CacheSize;
     if (total_mem_bytes) *total_mem_bytes = (int64_t)prop.totalGlobalMem;
+    return 0;
+}
+
+int dmx_host_gather_cb(const uint8_t* h_molecules_packed, int64_t n_molecules, int32_t* h_out_cb, int32_t n_threads) {
+    if (n_molecules <= 0) return 0;
+    DMX_REQUIRE(h_molecules_packed && h_out_cb, "null host pointer");
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 64) n_threads = 64;
+    const int64_t min_per_thread = 1 << 16;
+    if ((int64_t)n_threads * min_per_thread > n_molecules) n_threads = (int32_t)(n_molecules / min_per_thread) + 1;
+    auto work = [=](int64_t lo, int64_t hi) {
+        const uint8_t* src = h_molecules_packed + 12 * lo;  // record = (compressed_cb i4, compressed_ub i4, p f4)
+        for (int64_t k = lo; k < hi; ++k, src += 12) {
+            int32_t cb;
+            memcpy(&cb, src, 4);
+            h_out_cb[k] = cb;
+        }
+    };
+    if (n_threads == 1) {
+        work(0, n_molecules);
+        return 0;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(n_threads);
+    const int64_t per = (n_molecules + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; ++t) {
+        const int64_t lo = t * per, hi = lo + per < n_molecules ? lo + per : n_molecules;
+        if (lo < hi) pool.emplace_back(work, lo, hi);
+    }
+    for (auto& th : pool) th.join();
     return 0;
 }
 

@@ -25,8 +25,8 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
 }
 
 __global__ void unpack_match_kernel(const uint8_t* __restrict__ calls, int64_t n_calls,
-                                    const uint8_t* __restrict__ molecules, int64_t n_molecules, int64_t chrom_id,
-                                    const int64_t* __restrict__ gkeys, const int32_t* __restrict__ gvids,
+                                    const uint8_t* __restrict__ molecules, int64_t n_molecules, int molecule_stride,
+                                    int64_t chrom_id, const int64_t* __restrict__ gkeys, const int32_t* __restrict__ gvids,
                                     int64_t n_variants, int32_t* __restrict__ out_variant,
                                     int32_t* __restrict__ out_cb, float* __restrict__ out_e) {
     for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_calls;
@@ -40,7 +40,8 @@ __global__ void unpack_match_kernel(const uint8_t* __restrict__ calls, int64_t n
         int32_t variant = -1;
         int32_t cb = -1;
         if (mol >= 0 && (int64_t)mol < n_molecules) {
-            cb = *reinterpret_cast<const int32_t*>(molecules + 12 * (int64_t)mol);  // compressed_cb at offset 0
+            // compressed_cb: offset 0 of the 12-byte record, or a plain int32 array (stride 4, dmx_host_gather_cb)
+            cb = *reinterpret_cast<const int32_t*>(molecules + (int64_t)molecule_stride * mol);
             const int64_t key = (chrom_id << 40) | ((int64_t)pos << 8) | (int64_t)base;
             int64_t lo = 0, hi = n_variants;  // lower_bound
             while (lo < hi) {
@@ -227,14 +228,17 @@ static inline int grid_for(int64_t n, int threads) {
 extern "C" {
 
 int dmx_unpack_match_calls(const uint8_t* snp_calls_packed, int64_t n_calls, const uint8_t* molecules_packed,
-                           int64_t n_molecules, int64_t chrom_id, const int64_t* geno_keys_sorted,
+                           int64_t n_molecules, int32_t molecule_stride, int64_t chrom_id,
+                           const int64_t* geno_keys_sorted,
                            const int32_t* geno_vids_sorted, int64_t n_variants, int32_t* out_variant,
                            int32_t* out_cb, float* out_e, void* stream) {
     if (n_calls <= 0) return 0;
     DMX_REQUIRE(chrom_id >= 0 && chrom_id < (1ll << 22), "chrom_id %lld out of range", (long long)chrom_id);
+    DMX_REQUIRE(molecule_stride == 12 || molecule_stride == 4, "molecule_stride must be 12 (packed records) or 4");
     const int threads = 256;
     dmx::unpack_match_kernel<<<dmx::grid_for(n_calls, threads), threads, 0, (cudaStream_t)stream>>>(
-        snp_calls_packed, n_calls, molecules_packed, n_molecules, chrom_id, geno_keys_sorted, geno_vids_sorted,
+        snp_calls_packed, n_calls, molecules_packed, n_molecules, molecule_stride, chrom_id, geno_keys_sorted,
+        geno_vids_sorted,
         n_variants, out_variant, out_cb, out_e);
     DMX_LAUNCH_CHECK();
     return 0;

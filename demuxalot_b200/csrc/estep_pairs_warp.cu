@@ -73,19 +73,32 @@ struct WarpShape {
     static constexpr int RG = 32 / T;               // row groups in the warp
     static constexpr int LD = GP + 4;               // floats per staged row (bank-conflict-free row stride)
     static constexpr int QUADS = GP / 4;            // 16-byte pieces per row
-    static constexpr int QPS = NB;                  // quads per staging slot: half a row
 };
 
-template <int NB, int FLUSH_ROWS, bool ESUM16, int MIN_WARPS, int UNROLL>
-__global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const WarpPairsParams p) {
+// NB          blocks of 8 genotypes (G <= 8 NB)
+// FLUSH_ROWS  rows a lane multiplies into its products before the exponents are moved out (16, or 8 for tiny clips)
+// SR          rows per row group in one staged chunk (FLUSH_ROWS % SR == 0); the row loop over SR is fully unrolled
+// ESUM_SMEM   exponent sums live in shared memory (frees 32 registers -> more resident warps) instead of registers
+// PREFETCH    explicit register double buffer for the operands of the next row
+template <int NB, int FLUSH_ROWS, int SR, bool ESUM_SMEM, int MAX_REGS, bool PREFETCH>
+__global__ void __maxnreg__(MAX_REGS) estep_pairs_warp_kernel(const WarpPairsParams p) {
     using S = WarpShape<NB>;
-    constexpr int T = S::T, RG = S::RG, LD = S::LD, QPS = S::QPS;
-    constexpr int CHUNK = RG * FLUSH_ROWS;          // rows per staged chunk = one flush per lane
-    constexpr int SPL = (2 * CHUNK + 31) / 32;      // staging slots per lane and chunk
-    constexpr int DUMP_LD = 33;                     // epilogue dump: words per lane and array (+1: no bank conflicts)
+    constexpr int T = S::T, RG = S::RG, LD = S::LD, QUADS = S::QUADS;
+    constexpr int CHUNK = RG * SR;                  // rows per staged chunk
+    constexpr int CPF = FLUSH_ROWS / SR;            // chunks per flush
+    static_assert(FLUSH_ROWS % SR == 0, "FLUSH_ROWS must be a multiple of SR");
+    // staging slot = 1 / PIECES of a row; slot s of the chunk belongs to lane s % 32
+    constexpr int PIECES = (NB % 2 == 0 && (CHUNK * 2) % 32 != 0) ? 4 : 2;
+    constexpr int QPS = QUADS / PIECES;             // quads per slot
+    static_assert(QUADS % PIECES == 0, "row does not split into equal slots");
+    constexpr int RPP = 32 / PIECES;                // chunk rows covered by one pass of the warp
+    constexpr int SPL = (CHUNK * PIECES + 31) / 32; // staging slots per lane and chunk
+    constexpr int DUMP_LD = 33;                     // words per lane in the dump / exponent arrays (+1: no conflicts)
     constexpr int STAGE_FLOATS = 2 * CHUNK * LD;
-    constexpr int SMEM_FLOATS = STAGE_FLOATS > 3 * 32 * DUMP_LD ? STAGE_FLOATS : 3 * 32 * DUMP_LD;
+    constexpr int DUMP_FLOATS = (ESUM_SMEM ? 1 : 2) * 32 * DUMP_LD;
+    constexpr int SMEM_FLOATS = STAGE_FLOATS > DUMP_FLOATS ? STAGE_FLOATS : DUMP_FLOATS;
     __shared__ __align__(16) float smem[SMEM_FLOATS];
+    __shared__ unsigned esum_s[ESUM_SMEM ? 32 * DUMP_LD : 1];
     float* const stage0 = smem;
     float* const stage1 = smem + CHUNK * LD;
 
@@ -97,48 +110,49 @@ __global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const W
     const int seg = item - seg_first;
     const int64_t barcode = p.order ? (int64_t)__ldg(p.order + slot) : (int64_t)slot;
     const int64_t b_lo = __ldg(p.offsets + barcode), b_hi = __ldg(p.offsets + barcode + 1);
-    // segments: equal length, a multiple of CHUNK, so only the last one carries padding rows
-    const int64_t per = ((b_hi - b_lo + n_seg - 1) / n_seg + CHUNK - 1) / CHUNK * CHUNK;
+    // segments: equal length, a multiple of the flush period, so only the last one carries padding rows
+    constexpr int PERIOD = RG * FLUSH_ROWS;
+    const int64_t per = ((b_hi - b_lo + n_seg - 1) / n_seg + PERIOD - 1) / PERIOD * PERIOD;
     int64_t row_lo = b_lo + (int64_t)seg * per;
     if (row_lo > b_hi) row_lo = b_hi;
     const int64_t row_hi = row_lo + per < b_hi ? row_lo + per : b_hi;
     const int n_chunks = (int)((row_hi - row_lo + CHUNK - 1) / CHUNK);
 
-    // lane -> (row group, tile); lanes beyond RG * T shadow the last row group (they only stage and shuffle)
+    // lane -> (row group, tile); lanes beyond RG * T shadow the last row group (they only stage)
     int rg = lane / T;
     const int tile = lane - rg * T;
-    const bool has_tile = rg < RG;
-    if (!has_tile) rg = RG - 1;
+    if (rg >= RG) rg = RG - 1;
     int ti = 0, tj = tile;  // tile -> (I, J), I <= J, I-major
     while (tj >= NB - ti) { tj -= NB - ti; ++ti; }
     tj += ti;
 
-    uint64_t prod[4][8];                       // running products: [i pair][j], mantissas kept in [1, 2)
-    unsigned esum[ESUM16 ? 4 : 8][8];          // biased exponents moved out of the products
+    uint64_t prod[4][8];                  // running products: [i pair][j], mantissas kept in [1, 2) by the flushes
+    unsigned esum_r[ESUM_SMEM ? 1 : 4][8];  // 2 x 16-bit biased exponent sums per packed product (register flavour)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 8; ++b) prod[a][b] = wpack2(1.f, 1.f);
-#pragma unroll
-    for (int a = 0; a < (ESUM16 ? 4 : 8); ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) esum[a][b] = 0u;
+        for (int b = 0; b < 8; ++b) {
+            prod[a][b] = wpack2(1.f, 1.f);
+            if constexpr (ESUM_SMEM) esum_s[(a * 8 + b) * DUMP_LD + lane] = 0u;  // only ever touched by this lane
+            else esum_r[a][b] = 0u;
+        }
 
-    // ---- staging: slot k of a lane = half (lane & 1) of chunk row (lane >> 1) + 16 k -----------------------------
-    const int piece = lane & 1;
+    // ---- staging ---------------------------------------------------------------------------------------------------
+    const int piece = lane % PIECES;
+    const int row0 = lane / PIECES;
     const int n_table_quads = (int)(p.ld_table / 4);
     int v_pre[SPL];
     float e_pre[SPL], e_cur[SPL];
     unsigned live = 0;
 
     auto prefetch = [&](int chunk) {
-        const int64_t base = row_lo + (int64_t)chunk * CHUNK + (lane >> 1);
+        const int64_t base = row_lo + (int64_t)chunk * CHUNK + row0;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
-            const int64_t row = base + 16 * k;
+            const int64_t row = base + RPP * k;
             v_pre[k] = -1;
             e_pre[k] = 0.f;
-            if ((lane >> 1) + 16 * k < CHUNK && row < row_hi) {
+            if (row0 + RPP * k < CHUNK && row < row_hi) {
                 v_pre[k] = __ldg(p.variant + row);
                 e_pre[k] = __ldg(p.e + row);
             }
@@ -148,7 +162,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const W
         live = 0;
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
-            const int r = (lane >> 1) + 16 * k;
+            const int r = row0 + RPP * k;
             if (r < CHUNK) {
                 float* dst = buf + r * LD + 4 * QPS * piece;
                 e_cur[k] = e_pre[k];
@@ -173,19 +187,21 @@ __global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const W
 #pragma unroll
         for (int k = 0; k < SPL; ++k) {
             if (live & (1u << k)) {
-                float* dst = buf + ((lane >> 1) + 16 * k) * LD + 4 * QPS * piece;
+                float* dst = buf + (row0 + RPP * k) * LD + 4 * QPS * piece;
                 const float e = e_cur[k];
                 const float w = __fsub_rn(1.f, e);
                 const float ef = fmaxf(e, WARP_ERROR_FLOOR);
+                float4 x[QPS];  // all loads of the slot first: the fma chains then overlap
+#pragma unroll
+                for (int u = 0; u < QPS; ++u) x[u] = *reinterpret_cast<float4*>(dst + 4 * u);
 #pragma unroll
                 for (int u = 0; u < QPS; ++u) {
                     if (QPS * piece + u < n_table_quads) {
-                        float4 x = *reinterpret_cast<float4*>(dst + 4 * u);
-                        x.x = fmaf(x.x, w, ef);
-                        x.y = fmaf(x.y, w, ef);
-                        x.z = fmaf(x.z, w, ef);
-                        x.w = fmaf(x.w, w, ef);
-                        *reinterpret_cast<float4*>(dst + 4 * u) = x;
+                        x[u].x = fmaf(x[u].x, w, ef);
+                        x[u].y = fmaf(x[u].y, w, ef);
+                        x[u].z = fmaf(x[u].z, w, ef);
+                        x[u].w = fmaf(x[u].w, w, ef);
+                        *reinterpret_cast<float4*>(dst + 4 * u) = x[u];
                     }
                 }
             }
@@ -200,6 +216,7 @@ __global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const W
         __syncwarp();
     }
 
+    int n_flushes = 0;
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
         float* cur = (chunk & 1) ? stage1 : stage0;
         float* nxt = (chunk & 1) ? stage0 : stage1;
@@ -209,22 +226,11 @@ __global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const W
             if (chunk + 2 < n_chunks) prefetch(chunk + 2);
         }
 
-        // The row loop is deliberately NOT fully unrolled: 16 rows x 64 packed instructions are 25 KB of code per
-        // chunk and every warp of the SM sits at a different place in it, which made instruction fetch the top
-        // stall (ncu: no_instruction, 81 % i-cache hit rate).  UNROLL rows per iteration fit the L0 i-cache; the
-        // operands of the next row are loaded before the current one is consumed (register double buffer).
+        // The row loop covers SR (8) rows per chunk, not the whole flush period: 16 rows x 64 packed instructions were
+        // 25 KB of straight-line code with every warp of the SM at a different place in it, and instruction fetch
+        // became the top stall (ncu: no_instruction, 81 % i-cache hit rate).
         const float* rows = cur + rg * LD;
-        float4 i_lo = *reinterpret_cast<const float4*>(rows + 8 * ti);
-        float4 i_hi = *reinterpret_cast<const float4*>(rows + 8 * ti + 4);
-        float4 j_lo = *reinterpret_cast<const float4*>(rows + 8 * tj);
-        float4 j_hi = *reinterpret_cast<const float4*>(rows + 8 * tj + 4);
-#pragma unroll UNROLL
-        for (int k = 0; k < FLUSH_ROWS; ++k) {
-            const float* s = rows + (k + 1 < FLUSH_ROWS ? k + 1 : k) * (RG * LD);
-            const float4 n_i_lo = *reinterpret_cast<const float4*>(s + 8 * ti);
-            const float4 n_i_hi = *reinterpret_cast<const float4*>(s + 8 * ti + 4);
-            const float4 n_j_lo = *reinterpret_cast<const float4*>(s + 8 * tj);
-            const float4 n_j_hi = *reinterpret_cast<const float4*>(s + 8 * tj + 4);
+        auto row_updates = [&](const float4& i_lo, const float4& i_hi, const float4& j_lo, const float4& j_hi) {
             const uint64_t ai[4] = {wpack2(i_lo.x, i_lo.y), wpack2(i_lo.z, i_lo.w), wpack2(i_hi.x, i_hi.y),
                                     wpack2(i_hi.z, i_hi.w)};
             const float aj[8] = {j_lo.x, j_lo.y, j_lo.z, j_lo.w, j_hi.x, j_hi.y, j_hi.z, j_hi.w};
@@ -234,83 +240,105 @@ __global__ void __launch_bounds__(32, MIN_WARPS) estep_pairs_warp_kernel(const W
 #pragma unroll
                 for (int a = 0; a < 4; ++a) prod[a][b] = wmul2(prod[a][b], wadd2(ai[a], bj));
             }
-            i_lo = n_i_lo; i_hi = n_i_hi; j_lo = n_j_lo; j_hi = n_j_hi;
-        }
-        // renormalise: exponents into the integer sums, mantissas back to [1, 2) (exact)
+        };
+        if constexpr (PREFETCH) {  // operands of the next row are loaded before the current one is consumed
+            float4 i_lo = *reinterpret_cast<const float4*>(rows + 8 * ti);
+            float4 i_hi = *reinterpret_cast<const float4*>(rows + 8 * ti + 4);
+            float4 j_lo = *reinterpret_cast<const float4*>(rows + 8 * tj);
+            float4 j_hi = *reinterpret_cast<const float4*>(rows + 8 * tj + 4);
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                float lo, hi;
-                wunpack2(prod[a][b], lo, hi);
-                const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
-                if constexpr (ESUM16) {
-                    esum[a][b] += (blo >> 23) + ((bhi & 0x7f800000u) >> 7);
-                } else {
-                    esum[2 * a][b] += blo >> 23;
-                    esum[2 * a + 1][b] += bhi >> 23;
-                }
-                prod[a][b] = wpack2(__uint_as_float((blo & 0x007fffffu) | 0x3f800000u),
-                                    __uint_as_float((bhi & 0x007fffffu) | 0x3f800000u));
+            for (int k = 0; k < SR; ++k) {
+                const float* s = rows + (k + 1 < SR ? k + 1 : k) * (RG * LD);
+                const float4 n_i_lo = *reinterpret_cast<const float4*>(s + 8 * ti);
+                const float4 n_i_hi = *reinterpret_cast<const float4*>(s + 8 * ti + 4);
+                const float4 n_j_lo = *reinterpret_cast<const float4*>(s + 8 * tj);
+                const float4 n_j_hi = *reinterpret_cast<const float4*>(s + 8 * tj + 4);
+                row_updates(i_lo, i_hi, j_lo, j_hi);
+                i_lo = n_i_lo; i_hi = n_i_hi; j_lo = n_j_lo; j_hi = n_j_hi;
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SR; ++k) {
+                const float* s = rows + k * (RG * LD);
+                row_updates(*reinterpret_cast<const float4*>(s + 8 * ti), *reinterpret_cast<const float4*>(s + 8 * ti + 4),
+                            *reinterpret_cast<const float4*>(s + 8 * tj), *reinterpret_cast<const float4*>(s + 8 * tj + 4));
+            }
+        }
+        // renormalise every CPF chunks: exponents into the integer sums, mantissas back to [1, 2) (exact)
+        if (CPF == 1 || (chunk + 1) % CPF == 0) {
+            ++n_flushes;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    float lo, hi;
+                    wunpack2(prod[a][b], lo, hi);
+                    const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
+                    const unsigned add = (blo >> 23) + ((bhi & 0x7f800000u) >> 7);
+                    if constexpr (ESUM_SMEM) esum_s[(a * 8 + b) * DUMP_LD + lane] += add;
+                    else esum_r[a][b] += add;
+                    prod[a][b] = wpack2(__uint_as_float((blo & 0x007fffffu) | 0x3f800000u),
+                                        __uint_as_float((bhi & 0x007fffffu) | 0x3f800000u));
+                }
+        }
 
         if (more) land(nxt);
         __syncwarp();
     }
 
     // ---- epilogue -------------------------------------------------------------------------------------------------
-    // Every lane dumps its 64 (exponent sum, log2 mantissa) results into the now idle staging memory; then the warp
-    // walks the barcode's pairs as a rolled, lane-parallel loop: fixed-order sum over the row groups (deterministic),
-    // penalty, prior, one rounding to float32.  Runs of 8 consecutive columns are written together.
-    unsigned* dump_e = reinterpret_cast<unsigned*>(smem);
-    float* dump_lo = smem + 32 * DUMP_LD;
-    float* dump_hi = smem + 2 * 32 * DUMP_LD;
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            float lo, hi;
-            wunpack2(prod[a][b], lo, hi);
-            unsigned packed;
-            if constexpr (ESUM16) packed = esum[a][b];
-            else packed = (esum[2 * a][b] & 0xffffu) | (esum[2 * a + 1][b] << 16);
-            dump_e[lane * DUMP_LD + a * 8 + b] = packed;
-            dump_lo[lane * DUMP_LD + a * 8 + b] = wlg2(lo);
-            dump_hi[lane * DUMP_LD + a * 8 + b] = wlg2(hi);
-        }
-    __syncwarp();
-
+    // Every lane dumps its (exponent sums, log2 of the products) into shared memory (the staging area is idle now);
+    // then the warp walks the barcode's pairs as a rolled, lane-parallel loop: fixed-order sum over the row groups
+    // (deterministic), penalty, prior, one rounding to float32.  Runs of 8 consecutive columns are written together.
+    // The products may carry up to CPF - 1 unflushed chunks: lg2 of the whole float covers that.
     const int G = p.n_genotypes;
-    const int bias = 127 * n_chunks;
+    const int bias = 127 * n_flushes;
     const double padded_rows = (double)n_chunks * (double)CHUNK;
-#pragma unroll 1
-    for (int idx = lane; idx < T * 64; idx += 32) {
-        const int t = idx >> 6, q = idx & 63;
-        const int a = q >> 4, h = (q >> 3) & 1, b = q & 7;
-        int oi = 0, oj = t;
-        while (oj >= NB - oi) { oj -= NB - oi; ++oi; }
-        oj += oi;
-        const int i = 8 * oi + 2 * a + h, j = 8 * oj + b;
-        if (i < G && j < G && j >= i) {
-            double sum = 0.0;
+    unsigned* const dump_e = ESUM_SMEM ? esum_s : reinterpret_cast<unsigned*>(smem + 32 * DUMP_LD);
+    float* const dump_l = smem;
 #pragma unroll
-            for (int g = 0; g < RG; ++g) {
-                const int src = (g * T + t) * DUMP_LD + a * 8 + b;
-                const unsigned e2 = dump_e[src];
-                const int ev = (int)(h ? e2 >> 16 : e2 & 0xffffu) - bias;
-                sum += (double)ev + (double)(h ? dump_hi[src] : dump_lo[src]);
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                float lo, hi;
+                wunpack2(prod[a][b], lo, hi);
+                dump_l[(a * 8 + b) * DUMP_LD + lane] = wlg2(h ? hi : lo);
+                if constexpr (!ESUM_SMEM)
+                    if (h == 0) dump_e[(a * 8 + b) * DUMP_LD + lane] = esum_r[a][b];
             }
-            sum -= padded_rows;
-            const int64_t col = (i == j) ? i : (int64_t)G + (int64_t)i * G - (int64_t)i * (i + 1) / 2 + (j - i - 1);
-            if (n_seg == 1) {
-                const float pen = (i == j) ? 0.f : p.doublet_bonus;
-                float logit = (float)((double)pen + sum * 0.693147180559945309417232);
-                if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
-                p.logits[barcode * p.ld_logits + col] = logit;
-            } else {
-                p.partial[(int64_t)item * p.n_cols + col] = sum;
+        __syncwarp();
+#pragma unroll 1
+        for (int idx = lane; idx < T * 32; idx += 32) {
+            const int t = idx >> 5, q = idx & 31;
+            const int a = q >> 3, b = q & 7;
+            int oi = 0, oj = t;
+            while (oj >= NB - oi) { oj -= NB - oi; ++oi; }
+            oj += oi;
+            const int i = 8 * oi + 2 * a + h, j = 8 * oj + b;
+            if (i < G && j < G && j >= i) {
+                double sum = 0.0;
+#pragma unroll
+                for (int g = 0; g < RG; ++g) {
+                    const int src = (a * 8 + b) * DUMP_LD + g * T + t;
+                    const unsigned e2 = dump_e[src];
+                    const int ev = (int)(h ? e2 >> 16 : e2 & 0xffffu) - bias;
+                    sum += (double)ev + (double)dump_l[src];
+                }
+                sum -= padded_rows;
+                const int64_t col = (i == j) ? i : (int64_t)G + (int64_t)i * G - (int64_t)i * (i + 1) / 2 + (j - i - 1);
+                if (n_seg == 1) {
+                    const float pen = (i == j) ? 0.f : p.doublet_bonus;
+                    float logit = (float)((double)pen + sum * 0.693147180559945309417232);
+                    if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
+                    p.logits[barcode * p.ld_logits + col] = logit;
+                } else {
+                    p.partial[(int64_t)item * p.n_cols + col] = sum;
+                }
             }
         }
+        __syncwarp();
     }
 }
 
@@ -378,9 +406,9 @@ bool estep_pairs_warp_supported(int G, int flavour) {
     return nb == 3 || nb == 4 || nb == 5 || nb == 7;  // lane utilisation >= 28 / 32; other widths: estep_pairs.cu
 }
 
-template <int NB, int FLUSH_ROWS, bool ESUM16, int MIN_WARPS, int UNROLL>
+template <int NB, int FLUSH_ROWS, int SR, bool ESUM_SMEM, int MAX_REGS, bool PREFETCH>
 static int launch_warp_variant(const WarpPairsParams& p, int64_t n_items, cudaStream_t stream) {
-    auto kernel = estep_pairs_warp_kernel<NB, FLUSH_ROWS, ESUM16, MIN_WARPS, UNROLL>;
+    auto kernel = estep_pairs_warp_kernel<NB, FLUSH_ROWS, SR, ESUM_SMEM, MAX_REGS, PREFETCH>;
     DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   (int)cudaSharedmemCarveoutMaxShared));
     kernel<<<(unsigned)n_items, 32, 0, stream>>>(p);
@@ -416,21 +444,20 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
     const bool long_products = table_floor >= 0.0027f && warp_env_int("DMX_FLUSH_ROWS", 16) == 16;
     const int nb = (G + 7) / 8;
     const int variant = warp_env_int("DMX_WARP_VARIANT", 0);  // experiments: exponent packing / occupancy target
-#define DMX_WARP(NB_, E16_, MINW_, UNROLL_)                                                         \
-    return long_products ? launch_warp_variant<NB_, 16, E16_, MINW_, UNROLL_>(p, n_items, stream)   \
-                         : launch_warp_variant<NB_, 8, E16_, MINW_, UNROLL_>(p, n_items, stream)
+#define DMX_WARP(NB_, SR_, ESM_, REGS_, PF_)                                                                   \
+    return long_products ? launch_warp_variant<NB_, 16, SR_, ESM_, REGS_, PF_>(p, n_items, stream)            \
+                         : launch_warp_variant<NB_, 8, 8, ESM_, REGS_, PF_>(p, n_items, stream)
+    // measured on B200 at G = 32 (profiles/r01_sweep_warp_*.log): one 16-row chunk per flush and 12 resident warps per
+    // SM (168 registers, exponent sums in registers) 1.08 ms; 8-row chunks 1.19 ms (twice the chunk hand-overs);
+    // 16 warps per SM with the exponent sums in shared memory (128 registers) 1.17 ms
     switch (nb) {
-        case 3: DMX_WARP(3, true, 12, 2);
+        case 3: DMX_WARP(3, 16, false, 168, true);
         case 4:
-            if (variant == 1) { DMX_WARP(4, true, 12, 1); }
-            if (variant == 2) { DMX_WARP(4, true, 12, 4); }
-            if (variant == 3) { DMX_WARP(4, true, 12, 8); }
-            if (variant == 4) { DMX_WARP(4, true, 10, 2); }
-            if (variant == 5) { DMX_WARP(4, true, 14, 2); }
-            if (variant == 6) { DMX_WARP(4, true, 16, 2); }
-            DMX_WARP(4, true, 12, 2);
-        case 5: DMX_WARP(5, true, 12, 2);
-        case 7: DMX_WARP(7, true, 12, 2);
+            if (variant == 1) { DMX_WARP(4, 8, false, 168, true); }
+            if (variant == 2) { DMX_WARP(4, 8, true, 128, true); }
+            DMX_WARP(4, 16, false, 168, true);
+        case 5: DMX_WARP(5, 16, false, 168, true);
+        case 7: DMX_WARP(7, 16, false, 168, true);
         default: break;
     }
 #undef DMX_WARP

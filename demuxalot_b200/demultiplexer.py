@@ -16,6 +16,8 @@ Stage map (reference lines -> ABI call):
 from __future__ import annotations
 
 import ctypes as C
+import os
+import threading
 import warnings
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -47,6 +49,55 @@ def _to_device(array: np.ndarray, device) -> torch.Tensor:
         warnings.filterwarnings('ignore', message='The given NumPy array is not writable')
         host = torch.from_numpy(array)
     return host.to(device, non_blocking=True)
+
+
+_COPY_STREAMS: Dict[int, 'torch.cuda.Stream'] = {}
+
+
+def _copy_stream(device) -> 'torch.cuda.Stream':
+    """One side stream per device for host->device uploads that overlap the kernels of the current stream."""
+    key = torch.device(device).index
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
+def _upload_async(array: np.ndarray, device, copy_stream):
+    """Starts the upload on `copy_stream`; returns (tensor, event).  The consumer stream must wait for the event."""
+    consumer = torch.cuda.current_stream()
+    with torch.cuda.stream(copy_stream):
+        tensor = _to_device(array, device)
+        event = torch.cuda.Event()
+        event.record(copy_stream)
+    tensor.record_stream(consumer)  # allocated on the copy stream, read by kernels of the consumer stream
+    return tensor, event
+
+
+_CB_STAGING: Dict[int, dict] = {}
+
+
+def _cb_staging(device, n_int32: int) -> dict:
+    """Pinned host buffer (per device, grown on demand) through which the compressed_cb column travels, with the
+    event of the last upload that read it."""
+    key = torch.device(device).index
+    entry = _CB_STAGING.get(key)
+    if entry is None or entry['buffer'].numel() < n_int32:
+        if entry is not None and entry['last_read'] is not None:
+            entry['last_read'].synchronize()
+        entry = {'buffer': torch.empty(max(n_int32, 1), dtype=torch.int32, pin_memory=True), 'last_read': None}
+        _CB_STAGING[key] = entry
+    return entry
+
+
+def _device_index(index: dict, device) -> dict:
+    """Device copy of the genotype index (sorted keys, SNP CSR), cached with the host index it was made from."""
+    cache = index.setdefault('_device', {})
+    key = torch.device(device).index
+    if key not in cache:
+        cache[key] = {name: _to_device(index[name], device)
+                      for name in ('keys_sorted', 'vids_sorted', 'snp_offsets', 'snp_variants')}
+        torch.cuda.current_stream().synchronize()  # pageable source buffers: finish before anything reuses them
+    return cache[key]
 
 
 def _to_host(*tensors: torch.Tensor):
@@ -109,6 +160,15 @@ class DevicePack:
     variant2snp: np.ndarray
     raw_betas: torch.Tensor
     betas: torch.Tensor  # regularised betas (demux.py:388), float32 [V, G]
+    betas_min: Optional[torch.Tensor] = None  # min of the raw betas (device scalar), see check()
+
+    def check(self, betas_min=None) -> None:
+        """demux.py:374 -- negative betas are rejected.  Reads the device scalar unless the caller already
+        downloaded it together with its results (one synchronisation instead of two)."""
+        if betas_min is None and self.betas_min is not None:
+            betas_min = float(self.betas_min)
+        if betas_min is not None:
+            assert float(betas_min) >= 0, 'bad genotypes provided, negative betas appeared'
 
 
 class Demultiplexer:
@@ -127,7 +187,12 @@ class Demultiplexer:
     schedule_barcodes = True  # launch the deepest barcodes first (dmx_barcode_schedule)
     # warp-per-item pair E-step (dmx_estep_plan): barcodes deeper than this many rows are cut into segments
     # (16..4096); 0 disables the plan and every width runs on the CTA-per-barcode kernel
-    estep_segment_rows = 4096
+    estep_segment_rows = 2048
+    pipelined_upload = True  # host->device copies on a side stream, overlapping the unpack / row-builder kernels
+    # Only `compressed_cb` of the 12-byte molecule records is read (demux.py:352).  A pool of host threads copies that
+    # column into a pinned staging buffer while the snp_calls records are on the wire, and 4 instead of 12 bytes per
+    # molecule are uploaded.  0 threads: upload the records as they are.
+    host_gather_threads = min(16, max(1, (os.cpu_count() or 2) // 2))
     # variant-range tiles of the sharded M-step: all-reduce of tile k overlaps the M-step of tile k + 1.  Measured
     # (profiles/r01_allreduce_sweep_*.json): the 168 MB all-reduce is 0.34 ms over NVLink, every extra tile costs
     # ~0.25 ms of stream hand-over, so one tile wins; more tiles only pay off for tables of many GB.
@@ -169,10 +234,11 @@ class Demultiplexer:
 
         with torch.cuda.device(dev):
             stream = _stream()
-            gkeys = _to_device(index['keys_sorted'], dev)
-            gvids = _to_device(index['vids_sorted'], dev)
-            snp_offsets = _to_device(index['snp_offsets'], dev)
-            snp_variants = _to_device(index['snp_variants'], dev)
+            main = torch.cuda.current_stream()
+            copy_stream = _copy_stream(dev) if cls.pipelined_upload else main
+            dindex = _device_index(index, dev)
+            gkeys, gvids = dindex['keys_sorted'], dindex['vids_sorted']
+            snp_offsets, snp_variants = dindex['snp_offsets'], dindex['snp_variants']
 
             chrom2id = index['chrom2id']
             parts = []
@@ -188,24 +254,68 @@ class Demultiplexer:
             call_variant = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
             call_cb = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
             call_e = torch.empty(max(n_calls, 1), dtype=torch.float32, device=dev)
-            done = 0
-            for cid, calls in parts:
+            # All uploads are queued on the copy stream up front (chromosome records, then the betas); the unpack
+            # kernel of chromosome k runs on the main stream while chromosome k + 1 is still on the wire, and the
+            # row builder overlaps the upload of the betas.
+            gather = cls.host_gather_threads > 0 and len(parts) > 0
+            staging = ready_flags = worker = None
+            molecule_arrays = [_as_dtype(c.molecules[:c.n_molecules], MOLECULE_DTYPE) for _cid, c in parts]
+            if gather:
+                n_mols = [c.n_molecules for _cid, c in parts]
+                staging = _cb_staging(dev, sum(n_mols))
+                if staging['last_read'] is not None:
+                    staging['last_read'].synchronize()  # the previous call's upload out of this buffer is done
+                ready_flags = [threading.Event() for _ in parts]
+                base_ptr, n_threads = staging['buffer'].data_ptr(), int(cls.host_gather_threads)
+
+                def gather_all():  # ctypes releases the GIL: runs beside the upload submissions below
+                    offset = 0
+                    for k, mols in enumerate(molecule_arrays):
+                        rc = lib.dmx_host_gather_cb(mols.ctypes.data, len(mols), base_ptr + 4 * offset, n_threads)
+                        ready_flags[k].rc = rc
+                        ready_flags[k].set()
+                        offset += len(mols)
+
+                worker = threading.Thread(target=gather_all, daemon=True)
+                worker.start()
+            uploads = []
+            for (cid, calls), molecules in zip(parts, molecule_arrays):
                 snp_calls = _as_dtype(calls.snp_calls[:calls.n_snp_calls], SNP_CALL_DTYPE)
-                molecules = _as_dtype(calls.molecules[:calls.n_molecules], MOLECULE_DTYPE)
-                d_calls = _to_device(snp_calls, dev)
-                d_mols = _to_device(molecules, dev)
+                d_calls, ready = _upload_async(snp_calls, dev, copy_stream)
+                d_mols = None
+                if not gather:
+                    d_mols, ready = _upload_async(molecules, dev, copy_stream)
+                uploads.append([cid, calls, d_calls, d_mols, ready])
+            if gather:  # the compact columns follow the call records on the wire, in the order the gathers finish
+                offset = 0
+                for k, entry in enumerate(uploads):
+                    ready_flags[k].wait()
+                    _native.check(ready_flags[k].rc, 'dmx_host_gather_cb')
+                    n = entry[1].n_molecules
+                    with torch.cuda.stream(copy_stream):
+                        d_cb = staging['buffer'][offset:offset + n].to(dev, non_blocking=True)
+                        event = torch.cuda.Event()
+                        event.record(copy_stream)
+                    d_cb.record_stream(main)
+                    entry[3], entry[4] = d_cb, event
+                    staging['last_read'] = event
+                    offset += n
+                worker.join()
+            if raw.size:
+                raw_dev, raw_ready = _upload_async(raw, dev, copy_stream)
+            else:
+                raw_dev, raw_ready = torch.empty((n_variants, n_genotypes), device=dev), None
+            done = 0
+            for cid, calls, d_calls, d_mols, ready in uploads:
+                main.wait_event(ready)
                 n = calls.n_snp_calls
                 _native.check(lib.dmx_unpack_match_calls(
-                    d_calls.data_ptr(), n, d_mols.data_ptr(), calls.n_molecules, cid,
+                    d_calls.data_ptr(), n, d_mols.data_ptr(), calls.n_molecules, 4 if gather else 12, cid,
                     gkeys.data_ptr(), gvids.data_ptr(), n_variants,
                     call_variant[done:].data_ptr(), call_cb[done:].data_ptr(), call_e[done:].data_ptr(), stream),
                     'dmx_unpack_match_calls')
                 done += n
-                # d_calls / d_mols are released when they go out of scope; torch's caching allocator is
-                # stream-ordered, so reuse after the kernel above is safe.
-
-            raw_dev = _to_device(raw, dev) if raw.size else torch.empty((n_variants, n_genotypes), device=dev)
-            betas_min = raw_dev.min() if raw.size else None
+            del uploads  # the record buffers return to the allocator once the kernels that read them are done
 
             lo, hi = (0, n_barcodes) if barcode_range is None else barcode_range
             ws_bytes = lib.dmx_build_rows_workspace_bytes(n_calls, n_variants, n_barcodes)
@@ -243,8 +353,9 @@ class Demultiplexer:
                 import torch.distributed as dist
                 dist.all_reduce(n_mol, op=dist.ReduceOp.SUM, group=cls.process_group)
 
-            if betas_min is not None:  # demux.py:374; the value is ready, dmx_build_rows synchronised the stream
-                assert float(betas_min) >= 0, 'bad genotypes provided, negative betas appeared'
+            if raw_ready is not None:
+                main.wait_event(raw_ready)
+            betas_min = raw_dev.min() if raw.size else None  # demux.py:374, asserted by DevicePack.check()
             betas = torch.empty((n_variants, n_genotypes), dtype=torch.float32, device=dev)
             scratch = torch.empty(max(n_variants, 1), dtype=torch.float32, device=dev)
             _native.check(lib.dmx_prior_betas(
@@ -262,7 +373,8 @@ class Demultiplexer:
             csc_count=csc_count[:n_rows], variant_offsets=variant_offsets,
             csr_variant=csr_variant[:n_rows], csr_e=csr_e[:n_rows], csr_row=csr_row[:n_rows],
             barcode_offsets=barcode_offsets, barcode_order=barcode_order[:n_barcodes], n_mol=n_mol[:n_variants], snp_offsets=snp_offsets,
-            snp_variants=snp_variants, variant2snp=index['variant2snp'], raw_betas=raw_dev, betas=betas)
+            snp_variants=snp_variants, variant2snp=index['variant2snp'], raw_betas=raw_dev, betas=betas,
+            betas_min=betas_min)
 
     @classmethod
     def pack_calls(cls, chromosome2compressed_snp_calls, genotypes, add_data_prior: bool, n_barcodes: int = None):
@@ -277,6 +389,7 @@ class Demultiplexer:
             n_barcodes = 1 + max((int(c.molecules['compressed_cb'][:c.n_molecules].max())
                                   for c in chromosome2compressed_snp_calls.values() if c.n_molecules), default=0)
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, n_barcodes, add_data_prior)
+        pack.check()
         betas = pack.betas.cpu().numpy()
         betas.flags.writeable = False
         variant = pack.call_variant.cpu().numpy()
@@ -448,7 +561,9 @@ class Demultiplexer:
         table = cls._probs_table(pack, None, p_genotype_clip)
         table_is_finite = torch.isfinite(table).all()  # demux.py:135; read back together with the results
         logits, post, _ = cls._e_step(pack, table, doublet_prior)
-        logits_np, post_np, finite = _to_host(logits, post, table_is_finite)
+        extras = [table_is_finite] + ([pack.betas_min] if pack.betas_min is not None else [])
+        logits_np, post_np, finite, *betas_min = _to_host(logits, post, *extras)
+        pack.check(*betas_min)  # demux.py:374 (the reference asserts before computing; the result is the same)
         assert bool(finite), 'non-finite genotype probabilities'
         names = pd.Index(option_names(genotypes.genotype_names, doublet_prior))
         index = pd.Index(list(barcode_handler.ordered_barcodes), name='BARCODE')
@@ -480,6 +595,7 @@ class Demultiplexer:
             assert barcode_prior_logits.shape == (barcode_handler.n_barcodes, n_cols), 'wrong shape of priors'
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
                                 add_data_prior=True)
+        pack.check()
         prior_dev = cls._prior_logits_to_device(barcode_prior_logits, barcode_handler.n_barcodes, n_cols, pack.device)
         names = option_names(genotypes.genotype_names, doublet_prior)
         betas_host = pack.betas.cpu().numpy()
@@ -516,6 +632,7 @@ class Demultiplexer:
             assert barcode_prior_logits.shape == (barcode_handler.n_barcodes, n_cols), 'wrong shape of priors'
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
                                 add_data_prior=True)
+        pack.check()
         prior_dev = cls._prior_logits_to_device(barcode_prior_logits, barcode_handler.n_barcodes, n_cols, pack.device)
         post, addition = cls._em_iterations(pack, n_iterations, p_genotype_clip, doublet_prior, prior_dev)
         names = option_names(genotypes.genotype_names, doublet_prior)

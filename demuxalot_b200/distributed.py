@@ -100,6 +100,7 @@ def learn_genotypes_sharded(chromosome2compressed_snp_calls, genotypes, barcode_
                                               add_data_prior=True, barcode_range=(lo, hi))
         finally:
             Demultiplexer.process_group = saved
+        pack.check()
         prior_dev = Demultiplexer._prior_logits_to_device(barcode_prior_logits, n_barcodes, n_cols, pack.device)
         post, addition = Demultiplexer._em_iterations(pack, n_iterations, p_genotype_clip, doublet_prior, prior_dev)
     names = option_names(genotypes.genotype_names, doublet_prior)

@@ -44,12 +44,19 @@ int dmx_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int
  * builds key = chrom_id << 40 | pos << 8 | base and binary-searches it in the sorted genotype keys.
  * Writes, for call k, out_variant[k] (variant id or -1), out_cb[k] (molecules[mol].compressed_cb) and
  * out_e[k] (p_base_wrong, bit pattern preserved).
+ * `molecule_stride` = 12: molecules_packed holds the 12-byte records; 4: it holds only their compressed_cb column
+ * as a plain int32 array (what dmx_host_gather_cb produces: a third of the bytes on the wire).
  */
 int dmx_unpack_match_calls(const uint8_t* snp_calls_packed, int64_t n_calls,
-                           const uint8_t* molecules_packed, int64_t n_molecules,
+                           const uint8_t* molecules_packed, int64_t n_molecules, int32_t molecule_stride,
                            int64_t chrom_id,
                            const int64_t* geno_keys_sorted, const int32_t* geno_vids_sorted, int64_t n_variants,
                            int32_t* out_variant, int32_t* out_cb, float* out_e, void* stream);
+
+/* HOST function (both pointers are host memory): copies the compressed_cb column of n_molecules packed 12-byte
+ * molecule records (snp_counter.py:77-86) into a contiguous int32 array with n_threads threads, so that only the
+ * field the hot path reads (demux.py:352) is uploaded.  Pure data movement; no reference counterpart. */
+int dmx_host_gather_cb(const uint8_t* h_molecules_packed, int64_t n_molecules, int32_t* h_out_cb, int32_t n_threads);
 
 /* ---- (a3) group + UMI-combine: demux.py:276-300, 362-363, 381 ---------------------------------------
  * Input: molecule-level calls (variant or -1, barcode, p_base_wrong) in original call order.

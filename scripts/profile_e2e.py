@@ -79,7 +79,7 @@ stream = torch.cuda.current_stream().cuda_stream
 def unpack_all():
     done = 0
     for k, (a, m, c) in dcalls.items():
-        lib.dmx_unpack_match_calls(a.data_ptr(), c.n_snp_calls, m.data_ptr(), c.n_molecules, idx['chrom2id'][k], gkeys.data_ptr(),
+        lib.dmx_unpack_match_calls(a.data_ptr(), c.n_snp_calls, m.data_ptr(), c.n_molecules, 12, idx['chrom2id'][k], gkeys.data_ptr(),
                                    gvids.data_ptr(), len(idx['keys_sorted']), cv[done:].data_ptr(), cc[done:].data_ptr(), ce[done:].data_ptr(), stream)
         done += c.n_snp_calls
 

@@ -48,8 +48,8 @@ def run(seg_rows, env, reps=7, want_post=False):
 
 
 base = None
-cases = [(0, {})] + [(4096, dict(DMX_WARP_VARIANT=v)) for v in (0, 1, 2, 3, 4, 5, 6)] + \
-        [(2048, dict(DMX_WARP_VARIANT=0)), (4096, dict(DMX_FLUSH_ROWS=8))]
+cases = [(0, {})] + [(4096, dict(DMX_WARP_VARIANT=v)) for v in (0, 1, 2)] + \
+        [(2048, dict(DMX_WARP_VARIANT=0)), (1024, dict(DMX_WARP_VARIANT=0)), (4096, dict(DMX_FLUSH_ROWS=8))]
 for seg_rows, env in cases:
     try:
         best, mean, logits, n_items = run(seg_rows, env)

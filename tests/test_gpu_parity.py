@@ -296,6 +296,19 @@ def test_warp_pair_kernel_widths_and_segments(D, native_lib, shape, seg_rows):
     assert (np.abs(gb - ob) / np.maximum(np.abs(ob), 1e-3)).max() <= 1e-5
 
 
+def test_negative_betas_are_rejected(D):
+    """demux.py:374: `assert np.min(betas) >= 0` -- the device path checks the minimum it computed on upload."""
+    from demuxalot_b200.synthetic import make_dataset
+    ds = make_dataset(n_genotypes=4, n_snps=50, n_barcodes=10, rows_per_barcode=20, seed=3)
+    ds.genotypes.variant_betas[7, 2] = -0.5
+    with pytest.raises(AssertionError, match='negative betas'):
+        D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler)
+    with pytest.raises(AssertionError, match='negative betas'):
+        D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=2)
+    with pytest.raises(AssertionError, match='negative betas'):
+        next(D.staged_genotype_learning(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=2))
+
+
 def test_no_calls_and_unknown_chromosome(D):
     from demuxalot_b200 import CompressedSNPCalls
     case = load_case('g4_dp25')
