@@ -38,6 +38,10 @@ SIGNATURES = {
                             _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _ptr, _i64, _i32, _ptr]),
     'dmx_softmax_rows': (C.c_int, [_ptr, _i64, _i64, _i32, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     'dmx_mstep': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
+    'dmx_mstep_plan_bytes': (_i64, [_i64]),
+    'dmx_mstep_plan': (C.c_int, [_ptr, _i64, _i64, _ptr, _i64, C.POINTER(_i64), _ptr]),
+    'dmx_mstep_planned': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _i64, _i64,
+                                    _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr]),
     'dmx_round_f64_to_f32': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr]),
 }
 

@@ -188,6 +188,7 @@ class Demultiplexer:
     # warp-per-item pair E-step (dmx_estep_plan): barcodes deeper than this many rows are cut into segments
     # (16..4096); 0 disables the plan and every width runs on the CTA-per-barcode kernel
     estep_segment_rows = 2048
+    planned_mstep = True  # three-tier M-step schedule (dmx_mstep_plan); False: one warp per variant for all
     pipelined_upload = True  # host->device copies on a side stream, overlapping the unpack / row-builder kernels
     # Only `compressed_cb` of the 12-byte molecule records is read (demux.py:352).  A pool of host threads copies that
     # column into a pinned staging buffer while the snp_calls records are on the wire, and 4 instead of 12 bytes per
@@ -503,6 +504,26 @@ class Demultiplexer:
         return logits, post, singlets
 
     @classmethod
+    def _mstep_plan(cls, pack: DevicePack):
+        """Tier lists of the planned M-step (dmx_mstep_plan), computed once per pack; None when disabled."""
+        if not cls.planned_mstep or pack.n_variants == 0:
+            return None
+        cached = pack.__dict__.get('_mstep_plan')
+        if cached is None:
+            lib = _native.load()
+            dev = pack.device
+            plan_bytes = lib.dmx_mstep_plan_bytes(pack.n_rows)
+            plan = torch.empty(max(plan_bytes, 4), dtype=torch.uint8, device=dev)
+            counts = (C.c_int64 * 3)()
+            with torch.cuda.device(dev):
+                _native.check(lib.dmx_mstep_plan(pack.variant_offsets.data_ptr(), pack.n_variants, pack.n_rows,
+                                                 plan.data_ptr(), plan_bytes, counts, _stream()), 'dmx_mstep_plan')
+            n_medium, n_heavy_variants, n_heavy_items = (int(c) for c in counts)
+            scratch = torch.empty(max(n_heavy_items * pack.n_genotypes, 1), dtype=torch.float64, device=dev)
+            cached = pack.__dict__['_mstep_plan'] = (plan, n_medium, n_heavy_variants, n_heavy_items, scratch)
+        return cached
+
+    @classmethod
     def _m_step(cls, pack: DevicePack, singlets: torch.Tensor, out: Optional[torch.Tensor] = None,
                 out64: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(d) of north_star / demux.py:113-118 -> genotype_addition float32 [V, G] (+ all-reduce when sharded)."""
@@ -515,12 +536,20 @@ class Demultiplexer:
         if wide and out64 is None:
             out64 = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
+            plan = cls._mstep_plan(pack)
+
             def launch(v_lo: int, v_hi: int) -> None:
-                _native.check(lib.dmx_mstep(
-                    pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
-                    singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, float(cls.contribution_power),
-                    0 if wide else out.data_ptr(), pack.n_genotypes, _native.ptr(out64) if wide else 0,
-                    pack.n_genotypes, v_lo, v_hi, _stream()), 'dmx_mstep')
+                common = (pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
+                          singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, float(cls.contribution_power),
+                          0 if wide else out.data_ptr(), pack.n_genotypes, _native.ptr(out64) if wide else 0,
+                          pack.n_genotypes, v_lo, v_hi)
+                if plan is None:
+                    _native.check(lib.dmx_mstep(*common, _stream()), 'dmx_mstep')
+                else:
+                    blob, n_medium, n_heavy_variants, n_heavy_items, scratch = plan
+                    _native.check(lib.dmx_mstep_planned(*common, blob.data_ptr(), pack.n_rows, n_medium,
+                                                        n_heavy_variants, n_heavy_items, scratch.data_ptr(),
+                                                        _stream()), 'dmx_mstep_planned')
 
             if not sharded:
                 launch(0, pack.n_variants)

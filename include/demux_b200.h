@@ -165,6 +165,22 @@ int dmx_mstep(const int64_t* variant_offsets, const int32_t* csc_cb, const float
               float* addition, int64_t ld_addition, double* addition64, int64_t ld_addition64,
               int64_t variant_lo, int64_t variant_hi, void* stream);
 
+/* Planned M-step: same result as dmx_mstep, scheduled by rows per variant.  dmx_mstep_plan classifies the variants
+ * once per packed data set (the row counts do not change between EM iterations): variants with at most 128 rows are
+ * walked by groups of lanes in strict row order (np.bincount's order), longer ones by a warp each, and variants with
+ * more than 4096 rows are cut into chunks whose float64 partial sums are added in chunk order, so no work item is
+ * longer than 4096 rows.  `plan`: device buffer of dmx_mstep_plan_bytes(n_rows) bytes, opaque to the caller;
+ * h_counts[3] (host) receives n_medium, n_heavy_variants, n_heavy_items, to be passed back to dmx_mstep_planned
+ * together with a float64 scratch of n_heavy_items * n_genotypes elements.  dmx_mstep_plan synchronises `stream`. */
+int64_t dmx_mstep_plan_bytes(int64_t n_rows);
+int dmx_mstep_plan(const int64_t* variant_offsets, int64_t n_variants, int64_t n_rows, void* plan, int64_t plan_bytes,
+                   int64_t* h_counts, void* stream);
+int dmx_mstep_planned(const int64_t* variant_offsets, const int32_t* csc_cb, const float* csc_e,
+                      const float* singlet_posteriors, int64_t ld_singlet, int32_t n_genotypes, double power,
+                      float* addition, int64_t ld_addition, double* addition64, int64_t ld_addition64,
+                      int64_t variant_lo, int64_t variant_hi, const void* plan, int64_t n_rows, int64_t n_medium,
+                      int64_t n_heavy_variants, int64_t n_heavy_items, double* heavy_scratch, void* stream);
+
 /* float32(out) = float32(in64) elementwise over a [rows, cols] matrix (after an all-reduce of float64 partials) */
 int dmx_round_f64_to_f32(const double* in64, int64_t ld_in, float* out, int64_t ld_out, int64_t n_rows,
                          int32_t n_cols, void* stream);

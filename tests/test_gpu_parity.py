@@ -182,6 +182,53 @@ def test_m_step_bit_exact_given_identical_posteriors(D):
         D.contribution_power = 2.
 
 
+@pytest.mark.parametrize('G', [5, 32, 64, 200])
+def test_planned_m_step_tiers_vs_oracle_and_unplanned(D, G):
+    """Light / medium / heavy tiers of the planned M-step (few SNPs and many barcodes give variants with more than
+    4096 rows) against np.bincount's float64 sums and against the one-warp-per-variant schedule."""
+    import torch
+    from demuxalot_b200.synthetic import make_dataset
+    ds = make_dataset(n_genotypes=G, n_snps=60, n_barcodes=9000, rows_per_barcode=40, seed=41, depth_sigma=0.3)
+    B = ds.barcode_handler.n_barcodes
+    pack = D._pack_device(ds.calls, ds.genotypes, B, add_data_prior=True)
+    depth = np.diff(pack.variant_offsets.cpu().numpy())
+    plan = D._mstep_plan(pack)
+    assert plan[1] == int(((depth > 128) & (depth <= 4096)).sum())
+    assert plan[2] == int((depth > 4096).sum()) and plan[2] > 0 and plan[1] > 0 and (depth <= 128).any()
+    assert plan[3] == int(np.ceil(depth[depth > 4096] / 4096).sum())
+    rng = np.random.default_rng(3)
+    post = rng.dirichlet(np.full(G + 3, 0.3), size=B).astype(np.float32)[:, :G]
+    ld = D._table_ld(G)
+    singlets = torch.zeros((B, ld), dtype=torch.float32, device=pack.device)
+    singlets[:, :G] = torch.from_numpy(post).to(pack.device)
+    rows_v, rows_cb, rows_e = (t.cpu().numpy() for t in (pack.csc_variant, pack.csc_cb, pack.csc_e))
+    want = oracle.m_step(rows_v, rows_cb, rows_e, post, G, pack.n_variants, 2.)
+    got = D._m_step(pack, singlets).cpu().numpy()
+    assert np.array_equal(bits(got), bits(want))
+    half = pack.n_variants // 2  # variant-range tiling (the sharded M-step overlaps tiles with the all-reduce)
+    tiled = torch.full((pack.n_variants, G), -1.0, dtype=torch.float32, device=pack.device)
+    blob, n_medium, n_hv, n_hi, scratch = plan
+    lib = __import__('demuxalot_b200')._native.load()
+    for lo, hi in ((0, half), (half, pack.n_variants)):
+        assert lib.dmx_mstep_planned(pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
+                                     singlets.data_ptr(), ld, G, 2.0, tiled.data_ptr(), G, 0, G, lo, hi, blob.data_ptr(),
+                                     pack.n_rows, n_medium, n_hv, n_hi, scratch.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream) == 0
+    assert np.array_equal(bits(tiled.cpu().numpy()), bits(want))
+    try:
+        D.planned_mstep = False
+        plain = D._m_step(pack, singlets).cpu().numpy()
+        D.planned_mstep = True
+        D.contribution_power = 1.5
+        want15 = oracle.m_step(rows_v, rows_cb, rows_e, post, G, pack.n_variants, 1.5)
+        got15 = D._m_step(pack, singlets).cpu().numpy()
+    finally:
+        D.planned_mstep = True
+        D.contribution_power = 2.
+    assert np.array_equal(bits(plain), bits(want))
+    np.testing.assert_allclose(got15, want15, rtol=2e-6, atol=1e-12)
+
+
 def test_softmax_kernel_vs_scipy_formula(D, native_lib):
     import torch
     rng = np.random.default_rng(5)
