@@ -244,14 +244,15 @@ __global__ void mstep_plan_kernel(const int64_t* __restrict__ offsets, int64_t n
 }
 
 template <int LPR, int SLOTS, bool SQUARE, bool FULL>
-__global__ void __launch_bounds__(MSTEP_WARPS * 32) mstep_light_kernel(
-    const int64_t* __restrict__ offsets, const int32_t* __restrict__ cb_arr, const float* __restrict__ e_arr,
-    const float* __restrict__ post, int64_t ld_post, int n_genotypes, float power, float* __restrict__ addition,
-    int64_t ld_add, double* __restrict__ addition64, int64_t ld_add64, int64_t variant_lo, int64_t variant_hi) {
+__device__ __forceinline__ void mstep_light_body(
+    int64_t block, const int64_t* __restrict__ offsets, const int32_t* __restrict__ cb_arr,
+    const float* __restrict__ e_arr, const float* __restrict__ post, int64_t ld_post, int n_genotypes, float power,
+    float* __restrict__ addition, int64_t ld_add, double* __restrict__ addition64, int64_t ld_add64,
+    int64_t variant_lo, int64_t variant_hi) {
     constexpr int NG = 32 / LPR;  // variants processed side by side in a warp
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPR, grp = lane / LPR;
-    const int64_t warp_id = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t warp_id = (block * blockDim.x + threadIdx.x) >> 5;
     const int64_t v0 = variant_lo + warp_id * LIGHT_VPW;
     if (v0 >= variant_hi) return;
     const int count = (int)(variant_hi - v0 < LIGHT_VPW ? variant_hi - v0 : LIGHT_VPW);
@@ -352,13 +353,13 @@ __global__ void __launch_bounds__(MSTEP_WARPS * 32) mstep_light_kernel(
 
 // medium tier: one warp per listed variant
 template <int LPR, int SLOTS, bool SQUARE, bool FULL>
-__global__ void __launch_bounds__(MSTEP_WARPS * 32) mstep_medium_kernel(
-    const int32_t* __restrict__ list, int n_list, const int64_t* __restrict__ offsets, const int32_t* __restrict__ cb_arr,
-    const float* __restrict__ e_arr, const float* __restrict__ post, int64_t ld_post, int n_genotypes, float power,
-    float* __restrict__ addition, int64_t ld_add, double* __restrict__ addition64, int64_t ld_add64,
-    int64_t variant_lo, int64_t variant_hi) {
+__device__ __forceinline__ void mstep_medium_body(
+    int64_t block, const int32_t* __restrict__ list, int n_list, const int64_t* __restrict__ offsets,
+    const int32_t* __restrict__ cb_arr, const float* __restrict__ e_arr, const float* __restrict__ post,
+    int64_t ld_post, int n_genotypes, float power, float* __restrict__ addition, int64_t ld_add,
+    double* __restrict__ addition64, int64_t ld_add64, int64_t variant_lo, int64_t variant_hi) {
     const int lane = threadIdx.x & 31;
-    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t k = (block * blockDim.x + threadIdx.x) >> 5;
     if (k >= n_list) return;
     const int64_t v = list[k];
     if (v < variant_lo || v >= variant_hi) return;
@@ -374,14 +375,12 @@ __global__ void __launch_bounds__(MSTEP_WARPS * 32) mstep_medium_kernel(
 
 // heavy tier: one CTA per (variant, chunk of HEAVY_ROWS rows); float64 partial sums [n_items, G]
 template <int LPR, int SLOTS, bool SQUARE, bool FULL>
-__global__ void __launch_bounds__(MSTEP_WARPS * 32) mstep_heavy_chunk_kernel(
-    const int32_t* __restrict__ hv, const int32_t* __restrict__ item_hv, const int32_t* __restrict__ item_chunk,
-    const int64_t* __restrict__ offsets, const int32_t* __restrict__ cb_arr, const float* __restrict__ e_arr,
-    const float* __restrict__ post, int64_t ld_post, int n_genotypes, float power, double* __restrict__ scratch,
-    int64_t variant_lo, int64_t variant_hi) {
-    __shared__ double partial[MSTEP_WARPS][SLOTS * 4][32];
+__device__ __forceinline__ void mstep_heavy_chunk_body(
+    int item, double (*partial)[SLOTS * 4][32], const int32_t* __restrict__ hv, const int32_t* __restrict__ item_hv,
+    const int32_t* __restrict__ item_chunk, const int64_t* __restrict__ offsets, const int32_t* __restrict__ cb_arr,
+    const float* __restrict__ e_arr, const float* __restrict__ post, int64_t ld_post, int n_genotypes, float power,
+    double* __restrict__ scratch, int64_t variant_lo, int64_t variant_hi) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int item = blockIdx.x;
     const int64_t v = hv[item_hv[item]];
     if (v < variant_lo || v >= variant_hi) return;
     const int n_quads = (int)((ld_post + 3) / 4);
@@ -443,6 +442,32 @@ struct PlannedArgs {
     double* scratch;
 };
 
+// One launch for all tiers: the longest work items first (heavy chunks, then medium variants), the light variants
+// after them, so the tiers fill each other's stalls instead of running back to back (each alone is latency bound).
+template <int LPR, int SLOTS, bool SQUARE, bool FULL>
+__global__ void __launch_bounds__(MSTEP_WARPS * 32) mstep_tiers_kernel(
+    const int32_t* __restrict__ plan, MstepPlanLayout l, int n_medium, int n_heavy_items, int medium_blocks,
+    const int64_t* __restrict__ offsets, const int32_t* __restrict__ cb_arr, const float* __restrict__ e_arr,
+    const float* __restrict__ post, int64_t ld_post, int n_genotypes, float power, float* __restrict__ addition,
+    int64_t ld_add, double* __restrict__ addition64, int64_t ld_add64, double* __restrict__ scratch,
+    int64_t variant_lo, int64_t variant_hi) {
+    __shared__ double partial[MSTEP_WARPS][SLOTS * 4][32];
+    const int64_t b = blockIdx.x;
+    if (b < n_heavy_items) {
+        mstep_heavy_chunk_body<LPR, SLOTS, SQUARE, FULL>((int)b, partial, plan + l.off_hv, plan + l.off_item_hv,
+                                                         plan + l.off_item_chunk, offsets, cb_arr, e_arr, post, ld_post,
+                                                         n_genotypes, power, scratch, variant_lo, variant_hi);
+    } else if (b < n_heavy_items + medium_blocks) {
+        mstep_medium_body<LPR, SLOTS, SQUARE, FULL>(b - n_heavy_items, plan + l.off_medium, n_medium, offsets, cb_arr,
+                                                    e_arr, post, ld_post, n_genotypes, power, addition, ld_add, addition64,
+                                                    ld_add64, variant_lo, variant_hi);
+    } else {
+        mstep_light_body<LPR, SLOTS, SQUARE, FULL>(b - n_heavy_items - medium_blocks, offsets, cb_arr, e_arr, post, ld_post,
+                                                   n_genotypes, power, addition, ld_add, addition64, ld_add64, variant_lo,
+                                                   variant_hi);
+    }
+}
+
 template <int LPR, int SLOTS, bool SQUARE, bool FULL>
 static int launch_planned(cudaStream_t stream, const int64_t* offsets, const int32_t* cb, const float* e,
                           const float* post, int64_t ld_post, int G, float power, float* addition, int64_t ld_add,
@@ -450,22 +475,15 @@ static int launch_planned(cudaStream_t stream, const int64_t* offsets, const int
     const int threads = MSTEP_WARPS * 32;
     const int64_t n = v_hi - v_lo;
     const int64_t light_blocks = ceil_div(ceil_div(n, LIGHT_VPW), MSTEP_WARPS);
-    DMX_REQUIRE(light_blocks < (1ll << 31), "grid too large");
-    mstep_light_kernel<LPR, SLOTS, SQUARE, FULL><<<(unsigned)light_blocks, threads, 0, stream>>>(
-        offsets, cb, e, post, ld_post, G, power, addition, ld_add, addition64, ld_add64, v_lo, v_hi);
-    DMX_LAUNCH_CHECK();
+    const int64_t medium_blocks = ceil_div(pa.n_medium, MSTEP_WARPS);
+    const int64_t blocks = pa.n_heavy_items + medium_blocks + light_blocks;
+    DMX_REQUIRE(blocks < (1ll << 31), "grid too large");
     const MstepPlanLayout& l = pa.layout;
-    if (pa.n_medium > 0) {
-        mstep_medium_kernel<LPR, SLOTS, SQUARE, FULL><<<(unsigned)ceil_div(pa.n_medium, MSTEP_WARPS), threads, 0, stream>>>(
-            pa.plan + l.off_medium, pa.n_medium, offsets, cb, e, post, ld_post, G, power, addition, ld_add, addition64,
-            ld_add64, v_lo, v_hi);
-        DMX_LAUNCH_CHECK();
-    }
+    mstep_tiers_kernel<LPR, SLOTS, SQUARE, FULL><<<(unsigned)blocks, threads, 0, stream>>>(
+        pa.plan, l, pa.n_medium, pa.n_heavy_items, (int)medium_blocks, offsets, cb, e, post, ld_post, G, power, addition,
+        ld_add, addition64, ld_add64, pa.scratch, v_lo, v_hi);
+    DMX_LAUNCH_CHECK();
     if (pa.n_heavy_items > 0) {
-        mstep_heavy_chunk_kernel<LPR, SLOTS, SQUARE, FULL><<<(unsigned)pa.n_heavy_items, threads, 0, stream>>>(
-            pa.plan + l.off_hv, pa.plan + l.off_item_hv, pa.plan + l.off_item_chunk, offsets, cb, e, post, ld_post, G,
-            power, pa.scratch, v_lo, v_hi);
-        DMX_LAUNCH_CHECK();
         mstep_heavy_combine_kernel<<<(unsigned)pa.n_heavy_variants, 64, 0, stream>>>(
             pa.plan + l.off_hv, pa.plan + l.off_hv_first, pa.plan + l.off_hv_chunks, pa.n_heavy_variants, G, pa.scratch,
             addition, ld_add, addition64, ld_add64, v_lo, v_hi);
