@@ -11,6 +11,7 @@ from .barcodes import BarcodeHandler
 from .calls import CompressedSNPCalls
 from .counting import count_snps
 from .genotype_store import ProbabilisticGenotypes
+from .snp_detection import detect_snps_positions
 
 __version__ = '0.1.0'
 
@@ -23,4 +24,5 @@ def __getattr__(name):
     raise AttributeError(f'module {__name__!r} has no attribute {name!r}')
 
 
-__all__ = ['BarcodeHandler', 'CompressedSNPCalls', 'Demultiplexer', 'ProbabilisticGenotypes', 'count_snps']
+__all__ = ['BarcodeHandler', 'CompressedSNPCalls', 'Demultiplexer', 'ProbabilisticGenotypes', 'count_snps',
+           'detect_snps_positions']

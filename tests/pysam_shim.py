@@ -133,6 +133,34 @@ class AlignmentFile:
     def get_reference_length(self, reference: str) -> int:
         return self.lengths[self.references.index(reference)]
 
+    def count_coverage(self, contig, start=None, stop=None, quality_threshold=15, read_callback='all'):
+        """Plain per-base loop with pysam's documented semantics (aligned bases, base quality >= threshold, ACGT)."""
+        start = 0 if start is None else start
+        stop = self.get_reference_length(contig) if stop is None else stop
+        counts = {b: np.zeros(stop - start, dtype=np.int64) for b in 'ACGT'}
+        for read in self.fetch(contig, start, stop):
+            if read_callback == 'all':
+                if read.flag & (0x4 | 0x100 | 0x200 | 0x400):
+                    continue
+            elif read_callback != 'nofilter' and not read_callback(read):
+                continue
+            qpos, rpos = 0, read.reference_start
+            for op, length in read.cigartuples:
+                if op in (0, 7, 8):
+                    for k in range(length):
+                        r = rpos + k
+                        if start <= r < stop and read.query_qualities[qpos + k] >= quality_threshold:
+                            base = read.seq[qpos + k]
+                            if base in counts:
+                                counts[base][r - start] += 1
+                    qpos += length
+                    rpos += length
+                elif op in (1, 4):
+                    qpos += length
+                elif op in (2, 3):
+                    rpos += length
+        return tuple(counts[b] for b in 'ACGT')
+
     def fetch(self, contig=None, start=None, stop=None, **_kw) -> Iterator[AlignedSegment]:
         ids = range(len(self.references)) if contig is None else [self.references.index(contig)]
         for k in ids:
