@@ -187,7 +187,7 @@ class Demultiplexer:
     schedule_barcodes = True  # launch the deepest barcodes first (dmx_barcode_schedule)
     # warp-per-item pair E-step (dmx_estep_plan): barcodes deeper than this many rows are cut into segments
     # (16..4096); 0 disables the plan and every width runs on the CTA-per-barcode kernel
-    estep_segment_rows = 2048
+    estep_segment_rows = 4096
     planned_mstep = True  # three-tier M-step schedule (dmx_mstep_plan); False: one warp per variant for all
     pipelined_upload = True  # host->device copies on a side stream, overlapping the unpack / row-builder kernels
     # Only `compressed_cb` of the 12-byte molecule records is read (demux.py:352).  A pool of host threads copies that
