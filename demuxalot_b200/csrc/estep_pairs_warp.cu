@@ -23,6 +23,11 @@ namespace dmx {
 
 constexpr float WARP_ERROR_FLOOR = 1e-4f;
 
+static int warp_env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : fallback;
+}
+
 struct WarpPairsParams {
     const int64_t* offsets;     // barcode_offsets [B + 1]
     const int32_t* order;       // schedule slot -> barcode, or nullptr (identity)
@@ -40,6 +45,7 @@ struct WarpPairsParams {
     int64_t ld_logits;
     double* partial;  // [n_items, n_cols] log2-sums, written by the segments of multi-segment barcodes only
     int64_t n_cols;
+    unsigned mant_mask, one_bits;  // 0x007fffff, 0x3f800000: kernel parameters so that they stay in registers
 };
 
 __device__ __forceinline__ uint64_t wpack2(float lo, float hi) {
@@ -58,6 +64,12 @@ __device__ __forceinline__ uint64_t wadd2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ uint64_t wmul2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// (x & 0x007fffff) | 0x3f800000 as ONE LOP3 (the constants live in registers; with immediates ptxas emits two)
+__device__ __forceinline__ unsigned wreset_mantissa(unsigned bits, unsigned mant_mask, unsigned one_bits) {
+    unsigned d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(bits), "r"(mant_mask), "r"(one_bits));
     return d;
 }
 __device__ __forceinline__ float wlg2(float x) {
@@ -103,6 +115,7 @@ __global__ void __maxnreg__(MAX_REGS) estep_pairs_warp_kernel(const WarpPairsPar
     float* const stage1 = smem + CHUNK * LD;
 
     const int lane = threadIdx.x;
+    const unsigned mant_mask = p.mant_mask, one_bits = p.one_bits;
     const int item = blockIdx.x;
     const int slot = __ldg(p.item_slot + item);
     const int seg_first = __ldg(p.seg_prefix + slot);
@@ -274,11 +287,14 @@ __global__ void __maxnreg__(MAX_REGS) estep_pairs_warp_kernel(const WarpPairsPar
                     float lo, hi;
                     wunpack2(prod[a][b], lo, hi);
                     const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
-                    const unsigned add = (blo >> 23) + ((bhi & 0x7f800000u) >> 7);
-                    if constexpr (ESUM_SMEM) esum_s[(a * 8 + b) * DUMP_LD + lane] += add;
-                    else esum_r[a][b] += add;
-                    prod[a][b] = wpack2(__uint_as_float((blo & 0x007fffffu) | 0x3f800000u),
-                                        __uint_as_float((bhi & 0x007fffffu) | 0x3f800000u));
+                    if constexpr (ESUM_SMEM) {
+                        esum_s[(a * 8 + b) * DUMP_LD + lane] += (blo >> 23) + ((bhi >> 23) << 16);
+                    } else {
+                        esum_r[a][b] += blo >> 23;          // LEA.HI
+                        esum_r[a][b] += (bhi >> 23) << 16;  // SHF + LEA (the sign bit is clear)
+                    }
+                    prod[a][b] = wpack2(__uint_as_float(wreset_mantissa(blo, mant_mask, one_bits)),
+                                        __uint_as_float(wreset_mantissa(bhi, mant_mask, one_bits)));
                 }
         }
 
@@ -342,6 +358,293 @@ __global__ void __maxnreg__(MAX_REGS) estep_pairs_warp_kernel(const WarpPairsPar
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Many genotypes (G = 200: 325 tiles of 8 x 8): a warp cannot hold a barcode's whole triangle, so a work item is a
+// (barcode segment, PATCH) pair and a warp owns the 32 tiles of one patch.  Tiles are enumerated in bands of 4 tile
+// rows, column by column inside a band, and cut into consecutive runs of 32: a patch then touches at most 14 of the
+// 8-genotype blocks (4-8 row blocks + a contiguous run of column blocks), and only those operand blocks of each table
+// row are staged (compacted: block k of the patch's ascending block list sits at floats [8k, 8k + 8) of the staged
+// row).  Patches of one item are adjacent in the grid, so the warps that gather the same table rows run at the same
+// time and share them through L2.  Everything else -- arithmetic, flush, staging protocol, epilogue -- is the
+// warp kernel above with one row group.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int PATCH_BAND = 4;        // tile rows per band
+constexpr int PATCH_MAX_BLOCKS = 16; // operand blocks a patch may touch (checked by the launcher)
+constexpr int PATCH_LD = PATCH_MAX_BLOCKS * 8 + 4;
+
+// tile number g (band-major, column-major inside a band) -> (I, J)
+__host__ __device__ inline void patch_tile(int nb, int g, int* ti, int* tj) {
+    for (int i0 = 0; i0 < nb; i0 += PATCH_BAND) {
+        const int rows = nb - i0 < PATCH_BAND ? nb - i0 : PATCH_BAND;
+        const int cols = nb - i0;
+        // column c of the band (J = i0 + c) holds min(rows, c + 1) tiles
+        const int head = rows * (rows - 1) / 2;                           // tiles in the first rows - 1 columns
+        const int in_band = cols >= rows ? head + rows * (cols - rows + 1) : cols * (cols + 1) / 2;
+        if (g < in_band) {
+            int c = 0;
+            if (g < head) {
+                while (g >= c + 1) { g -= c + 1; ++c; }
+            } else {
+                g -= head;
+                c = rows - 1 + g / rows;
+                g -= (c - (rows - 1)) * rows;
+            }
+            *ti = i0 + g;
+            *tj = i0 + c;
+            return;
+        }
+        g -= in_band;
+    }
+    *ti = *tj = nb - 1;
+}
+
+template <int FLUSH_ROWS>
+__global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams p, int nb, int n_tiles, int n_patches) {
+    constexpr int CHUNK = FLUSH_ROWS;  // one row group: rows per staged chunk = rows per flush (<= 16)
+    constexpr int LD = PATCH_LD;
+    constexpr int DUMP_LD = 33;
+    constexpr int STAGE_FLOATS = 2 * CHUNK * LD;
+    constexpr int SMEM_FLOATS = STAGE_FLOATS > 2 * 32 * DUMP_LD ? STAGE_FLOATS : 2 * 32 * DUMP_LD;
+    __shared__ __align__(16) float smem[SMEM_FLOATS];
+    __shared__ int tile_ij[32];
+    float* const stage0 = smem;
+    float* const stage1 = smem + CHUNK * LD;
+
+    const int lane = threadIdx.x;
+    const unsigned mant_mask = p.mant_mask, one_bits = p.one_bits;
+    const int item = blockIdx.x / n_patches;
+    const int patch = blockIdx.x - item * n_patches;
+    const int slot = __ldg(p.item_slot + item);
+    const int seg_first = __ldg(p.seg_prefix + slot);
+    const int n_seg = __ldg(p.seg_prefix + slot + 1) - seg_first;
+    const int seg = item - seg_first;
+    const int64_t barcode = p.order ? (int64_t)__ldg(p.order + slot) : (int64_t)slot;
+    const int64_t b_lo = __ldg(p.offsets + barcode), b_hi = __ldg(p.offsets + barcode + 1);
+    const int64_t per = ((b_hi - b_lo + n_seg - 1) / n_seg + CHUNK - 1) / CHUNK * CHUNK;
+    int64_t row_lo = b_lo + (int64_t)seg * per;
+    if (row_lo > b_hi) row_lo = b_hi;
+    const int64_t row_hi = row_lo + per < b_hi ? row_lo + per : b_hi;
+    const int n_chunks = (int)((row_hi - row_lo + CHUNK - 1) / CHUNK);
+
+    // lane -> tile of the patch (lanes past the last tile shadow it: they stage and compute, but write nothing)
+    const int first_tile = patch * 32;
+    const int g = first_tile + lane < n_tiles ? first_tile + lane : n_tiles - 1;
+    int ti, tj;
+    patch_tile(nb, g, &ti, &tj);
+    tile_ij[lane] = first_tile + lane < n_tiles ? (ti | (tj << 8)) : -1;
+    const unsigned mask = __reduce_or_sync(0xffffffffu, (1u << ti) | (1u << tj));  // operand blocks of the patch
+    const int n_blocks = __popc(mask);
+    const int pos_i = __popc(mask & ((1u << ti) - 1u));  // where the lane's blocks sit in the staged rows
+    const int pos_j = __popc(mask & ((1u << tj) - 1u));
+
+    uint64_t prod[4][8];
+    unsigned esum[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            prod[a][b] = wpack2(1.f, 1.f);
+            esum[a][b] = 0u;
+        }
+
+    // ---- staging: lane = (chunk row lane >> 1, half lane & 1); a half = every other block of the patch's list ------
+    const int row_in_chunk = lane >> 1;
+    const int half = lane & 1;
+    const int n_table_quads = (int)(p.ld_table / 4);
+    int v_pre = -1;
+    float e_pre = 0.f, e_cur = 0.f;
+    bool live = false;
+
+    auto prefetch = [&](int chunk) {
+        const int64_t row = row_lo + (int64_t)chunk * CHUNK + row_in_chunk;
+        v_pre = -1;
+        e_pre = 0.f;
+        if (row_in_chunk < CHUNK && row < row_hi) {
+            v_pre = __ldg(p.variant + row);
+            e_pre = __ldg(p.e + row);
+        }
+    };
+    auto issue = [&](float* buf) {
+        live = false;
+        if (row_in_chunk < CHUNK) {
+            float* dst_row = buf + row_in_chunk * LD;
+            e_cur = e_pre;
+            live = v_pre >= 0;
+            const float* src_row = p.table + (int64_t)(live ? v_pre : 0) * p.ld_table;
+            unsigned m = mask;
+            for (int k = 0; m; ++k) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if ((k & 1) != half) continue;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    float* dst = dst_row + 8 * k + 4 * u;
+                    if (live && 2 * b + u < n_table_quads) cp_async_16(dst, src_row + 8 * b + 4 * u);
+                    else *reinterpret_cast<float4*>(dst) = make_float4(1.f, 1.f, 1.f, 1.f);  // padding row / column
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    auto land = [&](float* buf) {
+        cp_async_wait<0>();
+        if (live) {
+            float* dst_row = buf + row_in_chunk * LD;
+            const float w = __fsub_rn(1.f, e_cur);
+            const float ef = fmaxf(e_cur, WARP_ERROR_FLOOR);
+            unsigned m = mask;
+            for (int k = 0; m; ++k) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                if ((k & 1) != half) continue;
+                float4 x[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) x[u] = *reinterpret_cast<float4*>(dst_row + 8 * k + 4 * u);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (2 * b + u < n_table_quads) {
+                        x[u].x = fmaf(x[u].x, w, ef);
+                        x[u].y = fmaf(x[u].y, w, ef);
+                        x[u].z = fmaf(x[u].z, w, ef);
+                        x[u].w = fmaf(x[u].w, w, ef);
+                        *reinterpret_cast<float4*>(dst_row + 8 * k + 4 * u) = x[u];
+                    }
+                }
+            }
+        }
+    };
+
+    if (n_chunks > 0) {
+        prefetch(0);
+        issue(stage0);
+        if (n_chunks > 1) prefetch(1);
+        land(stage0);
+    }
+    __syncwarp();
+
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+        float* cur = (chunk & 1) ? stage1 : stage0;
+        float* nxt = (chunk & 1) ? stage0 : stage1;
+        const bool more = chunk + 1 < n_chunks;
+        if (more) {
+            issue(nxt);
+            if (chunk + 2 < n_chunks) prefetch(chunk + 2);
+        }
+        const float* oi = cur + 8 * pos_i;
+        const float* oj = cur + 8 * pos_j;
+        float4 i_lo = *reinterpret_cast<const float4*>(oi);
+        float4 i_hi = *reinterpret_cast<const float4*>(oi + 4);
+        float4 j_lo = *reinterpret_cast<const float4*>(oj);
+        float4 j_hi = *reinterpret_cast<const float4*>(oj + 4);
+#pragma unroll
+        for (int k = 0; k < CHUNK; ++k) {
+            const int kn = k + 1 < CHUNK ? k + 1 : k;
+            const float4 n_i_lo = *reinterpret_cast<const float4*>(oi + kn * LD);
+            const float4 n_i_hi = *reinterpret_cast<const float4*>(oi + kn * LD + 4);
+            const float4 n_j_lo = *reinterpret_cast<const float4*>(oj + kn * LD);
+            const float4 n_j_hi = *reinterpret_cast<const float4*>(oj + kn * LD + 4);
+            const uint64_t ai[4] = {wpack2(i_lo.x, i_lo.y), wpack2(i_lo.z, i_lo.w), wpack2(i_hi.x, i_hi.y),
+                                    wpack2(i_hi.z, i_hi.w)};
+            const float aj[8] = {j_lo.x, j_lo.y, j_lo.z, j_lo.w, j_hi.x, j_hi.y, j_hi.z, j_hi.w};
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const uint64_t bj = wpack2(aj[b], aj[b]);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) prod[a][b] = wmul2(prod[a][b], wadd2(ai[a], bj));
+            }
+            i_lo = n_i_lo; i_hi = n_i_hi; j_lo = n_j_lo; j_hi = n_j_hi;
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                float lo, hi;
+                wunpack2(prod[a][b], lo, hi);
+                const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
+                esum[a][b] += blo >> 23;
+                esum[a][b] += (bhi >> 23) << 16;
+                prod[a][b] = wpack2(__uint_as_float(wreset_mantissa(blo, mant_mask, one_bits)),
+                                    __uint_as_float(wreset_mantissa(bhi, mant_mask, one_bits)));
+            }
+        if (more) land(nxt);
+        __syncwarp();
+    }
+
+    // ---- epilogue (see the warp kernel): dump, then a rolled lane-parallel walk over the patch's pairs -------------
+    const int G = p.n_genotypes;
+    const int bias = 127 * n_chunks;
+    const double padded_rows = (double)n_chunks * (double)CHUNK;
+    unsigned* const dump_e = reinterpret_cast<unsigned*>(smem + 32 * DUMP_LD);
+    float* const dump_l = smem;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                float lo, hi;
+                wunpack2(prod[a][b], lo, hi);
+                dump_l[(a * 8 + b) * DUMP_LD + lane] = wlg2(h ? hi : lo);
+                if (h == 0) dump_e[(a * 8 + b) * DUMP_LD + lane] = esum[a][b];
+            }
+        __syncwarp();
+#pragma unroll 1
+        for (int idx = lane; idx < 32 * 32; idx += 32) {
+            const int t = idx >> 5, q = idx & 31;
+            const int a = q >> 3, b = q & 7;
+            const int ij = tile_ij[t];
+            if (ij < 0) continue;
+            const int i = 8 * (ij & 0xff) + 2 * a + h, j = 8 * (ij >> 8) + b;
+            if (i < G && j < G && j >= i) {
+                const int src = (a * 8 + b) * DUMP_LD + t;
+                const unsigned e2 = dump_e[src];
+                const int ev = (int)(h ? e2 >> 16 : e2 & 0xffffu) - bias;
+                const double sum = (double)ev + (double)dump_l[src] - padded_rows;
+                const int64_t col = (i == j) ? i : (int64_t)G + (int64_t)i * G - (int64_t)i * (i + 1) / 2 + (j - i - 1);
+                if (n_seg == 1) {
+                    const float pen = (i == j) ? 0.f : p.doublet_bonus;
+                    float logit = (float)((double)pen + sum * 0.693147180559945309417232);
+                    if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
+                    p.logits[barcode * p.ld_logits + col] = logit;
+                } else {
+                    p.partial[(int64_t)item * p.n_cols + col] = sum;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// patches of the band-major tile order: how many, and the largest operand-block list any of them needs
+static void patch_shape(int nb, int* n_tiles, int* n_patches, int* max_blocks) {
+    *n_tiles = nb * (nb + 1) / 2;
+    *n_patches = (*n_tiles + 31) / 32;
+    *max_blocks = 0;
+    for (int p = 0; p < *n_patches; ++p) {
+        unsigned mask = 0;
+        for (int l = 0; l < 32 && p * 32 + l < *n_tiles; ++l) {
+            int ti, tj;
+            patch_tile(nb, p * 32 + l, &ti, &tj);
+            mask |= (1u << ti) | (1u << tj);
+        }
+        int bits = 0;
+        for (unsigned m = mask; m; m &= m - 1) ++bits;
+        if (bits > *max_blocks) *max_blocks = bits;
+    }
+}
+
+static bool patch_kernel_supported(int G) {
+    const int nb = (G + 7) / 8;
+    // measured (scripts/sweep_estep_patch.py): +12 % over the CTA kernel at G = 200, where that kernel has to split a
+    // barcode's tiles over three CTAs; no gain at G = 104, where one CTA still covers a barcode
+    const int min_nb = warp_env_int("DMX_PAIRS_PATCH_MIN_NB", 17);
+    if (nb < min_nb || nb < 9 || nb > 32) return false;
+    if (warp_env_int("DMX_PAIRS_PATCH", 1) == 0) return false;
+    int n_tiles, n_patches, max_blocks;
+    patch_shape(nb, &n_tiles, &n_patches, &max_blocks);
+    return max_blocks <= PATCH_MAX_BLOCKS && 10 * n_tiles >= 8 * 32 * n_patches;  // >= 80 % of the lanes carry tiles
+}
+
 // ---- work items ---------------------------------------------------------------------------------------------------
 
 __global__ void plan_segments_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ order,
@@ -394,16 +697,12 @@ float pair_doublet_bonus(int n_genotypes, double dp) {  // demux.py:168-172
     return (float)bonus;
 }
 
-static int warp_env_int(const char* name, int fallback) {
-    const char* v = getenv(name);
-    return (v && *v) ? atoi(v) : fallback;
-}
-
 bool estep_pairs_warp_supported(int G, int flavour) {
     if (flavour != DMX_ESTEP_FAST) return false;
     if (warp_env_int("DMX_PAIRS_WARP", 1) == 0) return false;
     const int nb = (G + 7) / 8;
-    return nb == 3 || nb == 4 || nb == 5 || nb == 7;  // lane utilisation >= 28 / 32; other widths: estep_pairs.cu
+    if (nb == 3 || nb == 4 || nb == 5 || nb == 7) return true;  // lane utilisation >= 28 / 32
+    return patch_kernel_supported(G);                            // other widths: estep_pairs.cu
 }
 
 template <int NB, int FLUSH_ROWS, int SR, bool ESUM_SMEM, int MAX_REGS, bool PREFETCH>
@@ -440,6 +739,8 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
     p.ld_logits = ld_logits;
     p.partial = partial;
     p.n_cols = n_cols;
+    p.mant_mask = 0x007fffffu;
+    p.one_bits = 0x3f800000u;
     // 16 factors per product need 16 * -log2(2 (floor + 1e-4)) <= 120 binades; 8 factors are always safe
     const bool long_products = table_floor >= 0.0027f && warp_env_int("DMX_FLUSH_ROWS", 16) == 16;
     const int nb = (G + 7) / 8;
@@ -461,6 +762,25 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
         default: break;
     }
 #undef DMX_WARP
+    if (patch_kernel_supported(G)) {
+        int n_tiles, n_patches, max_blocks;
+        patch_shape(nb, &n_tiles, &n_patches, &max_blocks);
+        const int64_t grid = n_items * n_patches;
+        DMX_REQUIRE(grid < (1ll << 31), "grid too large");
+        if (long_products) {
+            auto kernel = estep_pairs_patch_kernel<16>;
+            DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+            kernel<<<(unsigned)grid, 32, 0, stream>>>(p, nb, n_tiles, n_patches);
+        } else {
+            auto kernel = estep_pairs_patch_kernel<8>;
+            DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+            kernel<<<(unsigned)grid, 32, 0, stream>>>(p, nb, n_tiles, n_patches);
+        }
+        DMX_LAUNCH_CHECK();
+        return 0;
+    }
     set_error("warp pair kernel does not support %d genotypes", G);
     return -2;
 }

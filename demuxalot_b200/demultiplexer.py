@@ -193,7 +193,8 @@ class Demultiplexer:
     # Only `compressed_cb` of the 12-byte molecule records is read (demux.py:352).  A pool of host threads copies that
     # column into a pinned staging buffer while the snp_calls records are on the wire, and 4 instead of 12 bytes per
     # molecule are uploaded.  0 threads: upload the records as they are.
-    host_gather_threads = min(16, max(1, (os.cpu_count() or 2) // 2))
+    # (default: half of the host cores, shared between the ranks of the node, at most 16)
+    host_gather_threads = min(16, max(1, (os.cpu_count() or 2) // (2 * max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1'))))))
     # variant-range tiles of the sharded M-step: all-reduce of tile k overlaps the M-step of tile k + 1.  Measured
     # (profiles/r01_allreduce_sweep_*.json): the 168 MB all-reduce is 0.34 ms over NVLink, every extra tile costs
     # ~0.25 ms of stream hand-over, so one tile wins; more tiles only pay off for tables of many GB.

@@ -297,6 +297,10 @@ WARP_SHAPES = [
     dict(n_genotypes=30, n_snps=2500, n_barcodes=120, rows_per_barcode=700, seed=33, shuffle_variants=True),
     dict(n_genotypes=37, n_snps=1200, n_barcodes=40, rows_per_barcode=180, seed=34),
     dict(n_genotypes=53, n_snps=1500, n_barcodes=30, rows_per_barcode=120, seed=35),
+    # patch kernel (a warp per 32-tile patch of the triangle): 18, 21 and 25 blocks of 8 genotypes
+    dict(n_genotypes=140, n_snps=1200, n_barcodes=20, rows_per_barcode=150, seed=36),
+    dict(n_genotypes=165, n_snps=900, n_barcodes=16, rows_per_barcode=90, seed=37, empty_barcode_fraction=0.2),
+    dict(n_genotypes=200, n_snps=1500, n_barcodes=16, rows_per_barcode=70, seed=38),
 ]
 
 
@@ -337,8 +341,11 @@ def test_warp_pair_kernel_widths_and_segments(D, native_lib, shape, seg_rows):
         assert rel.max() <= 2e-6
     finally:
         D.estep_segment_rows = old
-    gg, _ = D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4, doublet_prior=0.35)
-    og, _ = O.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4, doublet_prior=0.35)
+    if G > 64 and seg_rows != 4096:
+        return  # the EM comparison below does not depend on the segment length: once per width is enough
+    n_it = 4 if G <= 64 else 2
+    gg, _ = D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it, doublet_prior=0.35)
+    og, _ = O.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it, doublet_prior=0.35)
     ob, gb = np.array(og.get_betas(), np.float64), np.array(gg.get_betas(), np.float64)
     assert (np.abs(gb - ob) / np.maximum(np.abs(ob), 1e-3)).max() <= 1e-5
 

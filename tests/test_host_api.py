@@ -31,8 +31,12 @@ def test_abi_library_exports_every_declared_symbol(native_lib):
     assert native_lib.dmx_estep_workspace_bytes(10, 32, 0.35, 10, 0) == 0  # one item per barcode: no segment sums
     assert native_lib.dmx_estep_workspace_bytes(10, 32, 0.35, 14, 0) >= 14 * 528 * 8
     # widths served by the warp-per-item pair kernel (FAST flavour, doublet columns)
-    assert [g for g in range(1, 70) if native_lib.dmx_estep_plan_supported(g, 0.35, 1)] == \
-        list(range(17, 41)) + list(range(49, 57))
+    def blocks_ok(nb):  # widths of the patch kernel: at least 80 % of the lanes of its ceil(T / 32) warps carry tiles
+        tiles = nb * (nb + 1) // 2
+        return 17 <= nb <= 32 and 10 * tiles >= 8 * 32 * -(-tiles // 32)
+    want = [g for g in range(1, 270) if (g + 7) // 8 in (3, 4, 5, 7) or blocks_ok((g + 7) // 8)]
+    assert [g for g in range(1, 270) if native_lib.dmx_estep_plan_supported(g, 0.35, 1)] == want
+    assert 32 in want and 200 in want and 100 not in want and 64 not in want and 16 not in want
     assert not native_lib.dmx_estep_plan_supported(32, 0.0, 1) and not native_lib.dmx_estep_plan_supported(32, 0.35, 0)
 
 
