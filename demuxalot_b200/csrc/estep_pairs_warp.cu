@@ -447,9 +447,23 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
             esum[a][b] = 0u;
         }
 
-    // ---- staging: lane = (chunk row lane >> 1, half lane & 1); a half = every other block of the patch's list ------
+    // ---- staging: lane = (chunk row lane >> 1, half lane & 1); half 0 stages the first ceil(n / 2) blocks of the
+    // patch's ascending block list, half 1 the rest.  At most PATCH_MAX_BLOCKS / 2 blocks per lane: the loops below
+    // are straight-line predicated code with constant shared-memory offsets (the first version walked the whole list
+    // in a dynamic loop per chunk and spent more instructions on staging than on anything but the products).
+    constexpr int MAXB = PATCH_MAX_BLOCKS / 2;
     const int row_in_chunk = lane >> 1;
     const int half = lane & 1;
+    const int n_first = (n_blocks + 1) >> 1;
+    unsigned my_mask = mask;
+    {
+        unsigned first = 0, m = mask;
+        for (int k = 0; k < n_first; ++k) { first |= m & (0u - m); m &= m - 1; }
+        my_mask = half ? (mask & ~first) : first;
+    }
+    const int my_count = half ? n_blocks - n_first : n_first;
+    const int k0 = half ? n_first : 0;
+    const int full_blocks = (int)(p.ld_table / 8);  // blocks whose two quads both lie inside the table row
     const int n_table_quads = (int)(p.ld_table / 4);
     int v_pre = -1;
     float e_pre = 0.f, e_cur = 0.f;
@@ -467,20 +481,27 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
     auto issue = [&](float* buf) {
         live = false;
         if (row_in_chunk < CHUNK) {
-            float* dst_row = buf + row_in_chunk * LD;
+            float* dst = buf + row_in_chunk * LD + 8 * k0;
             e_cur = e_pre;
             live = v_pre >= 0;
             const float* src_row = p.table + (int64_t)(live ? v_pre : 0) * p.ld_table;
-            unsigned m = mask;
-            for (int k = 0; m; ++k) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                if ((k & 1) != half) continue;
+            unsigned m = my_mask;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    float* dst = dst_row + 8 * k + 4 * u;
-                    if (live && 2 * b + u < n_table_quads) cp_async_16(dst, src_row + 8 * b + 4 * u);
-                    else *reinterpret_cast<float4*>(dst) = make_float4(1.f, 1.f, 1.f, 1.f);  // padding row / column
+            for (int t = 0; t < MAXB; ++t) {
+                if (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float* src = src_row + 8 * b;
+                    if (live && b < full_blocks) {
+                        cp_async_16(dst + 8 * t, src);
+                        cp_async_16(dst + 8 * t + 4, src + 4);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            if (live && 2 * b + u < n_table_quads) cp_async_16(dst + 8 * t + 4 * u, src + 4 * u);
+                            else *reinterpret_cast<float4*>(dst + 8 * t + 4 * u) = make_float4(1.f, 1.f, 1.f, 1.f);
+                        }
+                    }
                 }
             }
         }
@@ -488,27 +509,19 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
     };
     auto land = [&](float* buf) {
         cp_async_wait<0>();
-        if (live) {
-            float* dst_row = buf + row_in_chunk * LD;
+        if (live) {  // columns past the table width hold 1 and get transformed too: no pair that uses them is written
+            float* dst = buf + row_in_chunk * LD + 8 * k0;
             const float w = __fsub_rn(1.f, e_cur);
             const float ef = fmaxf(e_cur, WARP_ERROR_FLOOR);
-            unsigned m = mask;
-            for (int k = 0; m; ++k) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1;
-                if ((k & 1) != half) continue;
-                float4 x[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) x[u] = *reinterpret_cast<float4*>(dst_row + 8 * k + 4 * u);
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (2 * b + u < n_table_quads) {
-                        x[u].x = fmaf(x[u].x, w, ef);
-                        x[u].y = fmaf(x[u].y, w, ef);
-                        x[u].z = fmaf(x[u].z, w, ef);
-                        x[u].w = fmaf(x[u].w, w, ef);
-                        *reinterpret_cast<float4*>(dst_row + 8 * k + 4 * u) = x[u];
-                    }
+            for (int t = 0; t < MAXB; ++t) {
+                if (t < my_count) {
+                    float4 x0 = *reinterpret_cast<float4*>(dst + 8 * t);
+                    float4 x1 = *reinterpret_cast<float4*>(dst + 8 * t + 4);
+                    x0.x = fmaf(x0.x, w, ef); x0.y = fmaf(x0.y, w, ef); x0.z = fmaf(x0.z, w, ef); x0.w = fmaf(x0.w, w, ef);
+                    x1.x = fmaf(x1.x, w, ef); x1.y = fmaf(x1.y, w, ef); x1.z = fmaf(x1.z, w, ef); x1.w = fmaf(x1.w, w, ef);
+                    *reinterpret_cast<float4*>(dst + 8 * t) = x0;
+                    *reinterpret_cast<float4*>(dst + 8 * t + 4) = x1;
                 }
             }
         }
