@@ -648,9 +648,9 @@ static void patch_shape(int nb, int* n_tiles, int* n_patches, int* max_blocks) {
 
 static bool patch_kernel_supported(int G) {
     const int nb = (G + 7) / 8;
-    // measured (scripts/sweep_estep_patch.py): +12 % over the CTA kernel at G = 200, where that kernel has to split a
-    // barcode's tiles over three CTAs; no gain at G = 104, where one CTA still covers a barcode
-    const int min_nb = warp_env_int("DMX_PAIRS_PATCH_MIN_NB", 17);
+    // measured against the CTA kernel (scripts/sweep_estep_patch.py, profiles/r01_sweep_patch_*.log):
+    // G = 104: 40.1 vs 30.2 updates/clk/SM, G = 128: 37.2 vs 27.2, G = 200: 39.9 vs 24.7
+    const int min_nb = warp_env_int("DMX_PAIRS_PATCH_MIN_NB", 9);
     if (nb < min_nb || nb < 9 || nb > 32) return false;
     if (warp_env_int("DMX_PAIRS_PATCH", 1) == 0) return false;
     int n_tiles, n_patches, max_blocks;

@@ -21,8 +21,8 @@ for G in widths:
     table = Demultiplexer._probs_table(pack, None, 0.01)
     print(f'G={G} C={C} B={n_barcodes} R={pack.n_rows} V={pack.n_variants} updates={pack.n_rows * C:.3e}', flush=True)
     base = None
-    for label, env, seg in (('CTA kernel', dict(DMX_PAIRS_PATCH=0), 4096), ('patch kernel', dict(DMX_PAIRS_PATCH=1, DMX_PAIRS_PATCH_MIN_NB=9), 4096),
-                            ('patch kernel seg 2048', dict(DMX_PAIRS_PATCH=1, DMX_PAIRS_PATCH_MIN_NB=9), 2048)):
+    for label, env, seg in (('CTA kernel', dict(DMX_PAIRS_PATCH=0), 4096), ('patch kernel', dict(DMX_PAIRS_PATCH=1), 4096),
+                            ('patch kernel seg 2048', dict(DMX_PAIRS_PATCH=1), 2048)):
         os.environ.update({k: str(v) for k, v in env.items()})
         Demultiplexer.estep_segment_rows = seg
         pack.__dict__.pop('_estep_plans', None)
