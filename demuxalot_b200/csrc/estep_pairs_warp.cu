@@ -1,4 +1,5 @@
-// Pair E-step, warp-autonomous flavour (FAST arithmetic, 17 <= G <= 56): one warp = one work item.
+// Pair E-step, warp-autonomous flavour (FAST arithmetic): one warp = one work item.  Two kernels: the warp kernel
+// (17 <= G <= 56, a warp holds a barcode's whole pair triangle) and, further down, the patch kernel (73 <= G <= 256).
 //
 //   S_b[i, j] = sum_{rows r of barcode b} log( 0.5 (P[v_r, i] + P[v_r, j]) (1 - e_r) + max(e_r, 1e-4) ),  i <= j
 //
@@ -513,16 +514,27 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
             float* dst = buf + row_in_chunk * LD + 8 * k0;
             const float w = __fsub_rn(1.f, e_cur);
             const float ef = fmaxf(e_cur, WARP_ERROR_FLOOR);
+            // two blocks per batch: all loads of a batch first (the operand registers of the row loop are dead
+            // here), so the fma chains do not each wait for their own shared-memory round trip
 #pragma unroll
-            for (int t = 0; t < MAXB; ++t) {
-                if (t < my_count) {
-                    float4 x0 = *reinterpret_cast<float4*>(dst + 8 * t);
-                    float4 x1 = *reinterpret_cast<float4*>(dst + 8 * t + 4);
-                    x0.x = fmaf(x0.x, w, ef); x0.y = fmaf(x0.y, w, ef); x0.z = fmaf(x0.z, w, ef); x0.w = fmaf(x0.w, w, ef);
-                    x1.x = fmaf(x1.x, w, ef); x1.y = fmaf(x1.y, w, ef); x1.z = fmaf(x1.z, w, ef); x1.w = fmaf(x1.w, w, ef);
-                    *reinterpret_cast<float4*>(dst + 8 * t) = x0;
-                    *reinterpret_cast<float4*>(dst + 8 * t + 4) = x1;
-                }
+            for (int t0 = 0; t0 < MAXB; t0 += 2) {
+                float4 x[4];
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    if (t0 + t < my_count) {
+                        x[2 * t] = *reinterpret_cast<float4*>(dst + 8 * (t0 + t));
+                        x[2 * t + 1] = *reinterpret_cast<float4*>(dst + 8 * (t0 + t) + 4);
+                    }
+#pragma unroll
+                for (int t = 0; t < 2; ++t)
+                    if (t0 + t < my_count) {
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            float4& v = x[2 * t + u];
+                            v.x = fmaf(v.x, w, ef); v.y = fmaf(v.y, w, ef); v.z = fmaf(v.z, w, ef); v.w = fmaf(v.w, w, ef);
+                            *reinterpret_cast<float4*>(dst + 8 * (t0 + t) + 4 * u) = v;
+                        }
+                    }
             }
         }
     };

@@ -115,14 +115,16 @@ def launch_shares(path: Path):
 if (SRC / 'launches.csv').exists():
     shutil.copy(SRC / 'launches.csv', OUT / f'{tag}_launches.csv')
     launch_shares(SRC / 'launches.csv')
-for rep, name in (('prof_estep_full.ncu-rep', 'estep_pairs'), ('prof_aux.ncu-rep', 'mstep_singlets_table_softmax')):
+for rep, name in (('prof_estep_full.ncu-rep', 'estep_pairs'), ('prof_aux.ncu-rep', 'mstep_singlets_table_softmax'),
+                  ('prof_patch.ncu-rep', 'estep_pairs_patch_g200'), ('prof_singlets.ncu-rep', 'estep_singlets'),
+                  ('r01b_mstep_light.ncu-rep', 'mstep_light_tier')):
     if (SRC / rep).exists():
         traffic = summarise_report(SRC / rep, name)
         if name == 'estep_pairs' and traffic:
             (OUT / 'estep_traffic.json').write_text(json.dumps({
                 'kernel': 'estep_pairs_warp_kernel', 'dram_bytes_per_launch': traffic, 'source': f'{tag}_ncu_{name}.txt',
                 'workload': 'pbmc_32 scale 1.0 (R = 20.07 M rows, G = 32)'}) + '\n')
-for f in ('microbench.log', 'microbench_packed_tile.log', 'bench_mstep.log', 'parity_report.json', 'profile_e2e.log', 'bench.log', 'bench_n2.log', 'bench_n8.log',
+for f in ('microbench.log', 'microbench_packed_tile.log', 'bench_mstep.log', 'config4_shard.log', 'parity_report.json', 'profile_e2e.log', 'bench.log', 'bench_n2.log', 'bench_n8.log',
           'bench_reference.log', 'sweep_g32_c.log', 'sweep_g200_c.log', 'sanitizer.log', 'pytest_gpu.log',
           'pytest_dist.log'):
     if (SRC / f).exists():

@@ -14,6 +14,9 @@ ncu --set full --clock-control none --import-source on -k 'regex:mstep_tiers|pro
     python scripts/profile_estep.py 1.0 1 > gpurun_out/ncu_aux.log 2>&1
 ncu --set full --clock-control none -k regex:estep_singlets -c 1 -f -o gpurun_out/prof_singlets \
     python scripts/profile_estep.py 1.0 1 0.0 > gpurun_out/ncu_singlets.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:estep_pairs_patch -c 1 -f -o gpurun_out/prof_patch \
+    python scripts/sweep_estep_patch.py 200 > gpurun_out/ncu_patch.log 2>&1
+python scripts/run_config4_shard.py > gpurun_out/config4_shard.log 2>&1
 python scripts/profile_e2e.py > gpurun_out/profile_e2e.log 2>&1
 python scripts/bench_mstep.py > gpurun_out/bench_mstep.log 2>&1
 timeout 600 compute-sanitizer --tool memcheck python __graft_entry__.py smoke 2>&1 | tail -15 > gpurun_out/sanitizer.log
