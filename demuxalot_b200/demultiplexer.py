@@ -273,9 +273,12 @@ class Demultiplexer:
                 def gather_all():  # ctypes releases the GIL: runs beside the upload submissions below
                     offset = 0
                     for k, mols in enumerate(molecule_arrays):
-                        rc = lib.dmx_host_gather_cb(mols.ctypes.data, len(mols), base_ptr + 4 * offset, n_threads)
-                        ready_flags[k].rc = rc
-                        ready_flags[k].set()
+                        rc = -1  # whatever happens the flag is set, so the consumer below never waits for ever
+                        try:
+                            rc = lib.dmx_host_gather_cb(mols.ctypes.data, len(mols), base_ptr + 4 * offset, n_threads)
+                        finally:
+                            ready_flags[k].rc = rc
+                            ready_flags[k].set()
                         offset += len(mols)
 
                 worker = threading.Thread(target=gather_all, daemon=True)

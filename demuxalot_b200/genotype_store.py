@@ -92,8 +92,15 @@ class ProbabilisticGenotypes:
         memo[id(self)] = out
         for name, value in self.__dict__.items():
             if name == '_hot_index_cache':
-                continue  # the copy may diverge; rebuild lazily
+                continue  # carried over below
+            if name == 'var2varid':
+                out.var2varid = dict(value)  # keys are immutable (chrom, pos, base) tuples: no need to recurse
+                continue
             setattr(out, name, deepcopy(value, memo))
+        cached = self.__dict__.get('_hot_index_cache')
+        if cached is not None and cached['stamp'] == (id(self.var2varid), len(self.var2varid)):
+            # same variants, same index (its arrays are never written); it is dropped as soon as the copy grows
+            out.__dict__['_hot_index_cache'] = dict(cached, stamp=(id(out.var2varid), len(out.var2varid)))
         return out
 
     def _with_betas(self, external_betas: np.ndarray) -> 'ProbabilisticGenotypes':
@@ -121,21 +128,28 @@ class ProbabilisticGenotypes:
         if cached is not None and cached['stamp'] == stamp:
             return cached
         n = len(self.var2varid)
-        keys = np.empty(n, dtype=np.int64)
-        vids = np.empty(n, dtype=np.int32)
-        variant2snp = np.full(n, -1, dtype=np.int32)
-        chrom2id: Dict[object, int] = {}
-        snp2id: Dict[Tuple, int] = {}
-        for k, ((chrom, pos, base), vid) in enumerate(self.var2varid.items()):
-            cid = chrom2id.setdefault(chrom, len(chrom2id))
-            keys[k] = (cid << 40) | ((int(pos) & 0xFFFFFFFF) << 8) | BASE_TO_INDEX[base]
-            vids[k] = vid
-            variant2snp[vid] = snp2id.setdefault((chrom, pos), len(snp2id))
+        # vectorised: the per-item Python loop cost 2.9 s at 5 M variants (factorize numbers in first-seen order,
+        # exactly what the reference's setdefault(len(...)) loops do, genotypes.py:56-66)
+        if n:
+            chroms, positions, bases = zip(*self.var2varid.keys())
+            vids = np.fromiter(self.var2varid.values(), dtype=np.int64, count=n)
+            chrom_codes, chrom_names = pd.factorize(np.asarray(chroms, dtype=object), sort=False)
+            pos = np.asarray(positions, dtype=np.int64)
+            base_codes = np.fromiter((BASE_TO_INDEX[b] for b in bases), dtype=np.int64, count=n)
+        else:
+            vids = pos = base_codes = chrom_codes = np.zeros(0, dtype=np.int64)
+            chrom_names = []
+        chrom2id: Dict[object, int] = {name: k for k, name in enumerate(chrom_names)}
+        keys = (chrom_codes.astype(np.int64) << 40) | ((pos & 0xFFFFFFFF) << 8) | base_codes
+        snp_codes, snp_uniques = pd.factorize((chrom_codes.astype(np.int64) << 40) | (pos & 0xFFFFFFFFFF), sort=False)
         # demux.py:317-318 -- ids must enumerate the rows of variant_betas
         assert np.array_equal(np.sort(vids), np.arange(n)), 'variant ids must be a permutation of 0..V-1'
+        variant2snp = np.full(n, -1, dtype=np.int32)
+        variant2snp[vids] = snp_codes
         assert np.all(variant2snp >= 0)
+        vids = vids.astype(np.int32)
         order = np.argsort(keys, kind='stable')
-        n_snps = len(snp2id)
+        n_snps = len(snp_uniques)
         snp_variants = np.argsort(variant2snp, kind='stable').astype(np.int32)
         snp_offsets = np.zeros(n_snps + 1, dtype=np.int32)
         np.cumsum(np.bincount(variant2snp, minlength=n_snps), out=snp_offsets[1:])
