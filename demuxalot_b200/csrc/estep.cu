@@ -279,7 +279,8 @@ int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int
 }
 
 int dmx_estep_plan_supported(int32_t n_genotypes, double doublet_prior, int32_t flavour) {
-    return doublet_prior != 0 && dmx::estep_pairs_warp_supported(n_genotypes, flavour) ? 1 : 0;
+    if (!dmx::estep_pairs_warp_supported(n_genotypes, flavour)) return 0;
+    return (doublet_prior != 0 || n_genotypes <= 8) ? 1 : 0;  // singlets only: the lane-per-row kernel (G <= 8)
 }
 
 int64_t dmx_estep_plan_workspace_bytes(int64_t n_barcodes) {
@@ -334,7 +335,7 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
     const int64_t n_cols = doublet_prior == 0 ? G : (int64_t)G * (G + 1) / 2;
     DMX_REQUIRE(n_cols < (1ll << 31), "too many columns");
 
-    const bool planned = seg_prefix && item_slot && n_items > 0 && doublet_prior != 0 &&
+    const bool planned = seg_prefix && item_slot && n_items > 0 && (doublet_prior != 0 || G <= 8) &&
                          estep_pairs_warp_supported(G, flavour);
     uint8_t* ws = (uint8_t*)workspace;
     int64_t ws_left = workspace ? workspace_bytes : 0;
@@ -354,7 +355,7 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
         partial = (double*)ws;
     }
 
-    if (doublet_prior == 0) {
+    if (doublet_prior == 0 && !planned) {
         int rc;
         if (flavour == DMX_ESTEP_FAST)
             rc = launch_singlets<DMX_ESTEP_FAST>((unsigned)n_barcodes, stream, barcode_offsets, barcode_order, csr_variant,
@@ -376,7 +377,7 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
             cp.prior = prior_logits;
             cp.ld_prior = ld_prior;
             cp.n_singlets = G;
-            cp.doublet_bonus = pair_doublet_bonus(G, doublet_prior);
+            cp.doublet_bonus = doublet_prior == 0 ? 0.f : pair_doublet_bonus(G, doublet_prior);
             return launch_softmax(out_logits, ld_out, n_barcodes, (int)n_cols, posteriors, ld_post, singlet_posteriors,
                                   ld_singlet, G, stream, &cp);
         }

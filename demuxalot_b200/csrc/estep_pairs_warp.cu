@@ -1,5 +1,6 @@
 // Pair E-step, warp-autonomous flavour (FAST arithmetic): one warp = one work item.  Two kernels: the warp kernel
-// (17 <= G <= 56, a warp holds a barcode's whole pair triangle) and, further down, the patch kernel (73 <= G <= 256).
+// (17 <= G <= 56, a warp holds a barcode's whole pair triangle), the patch kernel (73 <= G <= 256) and the lane-per-row
+// kernel for G <= 8, further down.
 //
 //   S_b[i, j] = sum_{rows r of barcode b} log( 0.5 (P[v_r, i] + P[v_r, j]) (1 - e_r) + max(e_r, 1e-4) ),  i <= j
 //
@@ -670,6 +671,111 @@ static bool patch_kernel_supported(int G) {
     return max_blocks <= PATCH_MAX_BLOCKS && 10 * n_tiles >= 8 * 32 * n_patches;  // >= 80 % of the lanes carry tiles
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Few genotypes (G <= 8, at most 36 columns; the reference's own example has 4): a row feeds too few pairs for
+// register tiles shared across lanes, and the kernel is bound by the row stream, not by arithmetic.  Here a LANE owns
+// whole rows: lane l of the item's warp takes rows l, l + 32, ... (coalesced record loads, one or two 128-bit gathers
+// of the table row), keeps all GT (GT + 1) / 2 running products of its rows in registers with the same exponent
+// bookkeeping, and the 32 lanes are combined at the end with an xor-shuffle tree in float64 (fixed order:
+// deterministic).  Rows past the end multiply by exactly 1.  Same work items as the other warp kernels.
+// ---------------------------------------------------------------------------------------------------------------
+// SINGLETS: doublet_prior == 0 -- only the G singlet columns, factor a_g itself (no pair sum, no factor 2).
+template <int GT, int FLUSH_ROWS, bool SINGLETS>
+__global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsParams p) {
+    constexpr int CT = SINGLETS ? GT : GT * (GT + 1) / 2;
+    constexpr int WAVES = 4;  // rows in flight per lane
+    const int lane = threadIdx.x;
+    const int item = blockIdx.x;
+    const int slot = __ldg(p.item_slot + item);
+    const int seg_first = __ldg(p.seg_prefix + slot);
+    const int n_seg = __ldg(p.seg_prefix + slot + 1) - seg_first;
+    const int seg = item - seg_first;
+    const int64_t barcode = p.order ? (int64_t)__ldg(p.order + slot) : (int64_t)slot;
+    const int64_t b_lo = __ldg(p.offsets + barcode), b_hi = __ldg(p.offsets + barcode + 1);
+    const int64_t per = ((b_hi - b_lo + n_seg - 1) / n_seg + 31) / 32 * 32;
+    int64_t row_lo = b_lo + (int64_t)seg * per;
+    if (row_lo > b_hi) row_lo = b_hi;
+    const int64_t row_hi = row_lo + per < b_hi ? row_lo + per : b_hi;
+
+    float prod[CT];
+    int esum[CT];
+#pragma unroll
+    for (int c = 0; c < CT; ++c) { prod[c] = 1.f; esum[c] = 0; }
+    int n_flushes = 0, since_flush = 0;
+
+    for (int64_t base = row_lo + lane; base < row_hi; base += 32 * WAVES) {  // lanes run out of rows at different times
+        float a[WAVES][GT];
+#pragma unroll
+        for (int u = 0; u < WAVES; ++u) {
+            const int64_t row = base + 32 * u;
+            const bool ok = row < row_hi;
+            const int32_t v = ok ? __ldg(p.variant + row) : 0;
+            const float e = ok ? __ldg(p.e + row) : 0.f;
+            const float w = __fsub_rn(1.f, e);
+            const float ef = fmaxf(e, WARP_ERROR_FLOOR);
+            const float4* src = reinterpret_cast<const float4*>(p.table + (int64_t)v * p.ld_table);
+#pragma unroll
+            for (int q = 0; q < (GT + 3) / 4; ++q) {
+                float4 t = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (ok && 4 * q < p.ld_table) t = __ldg(src + q);
+                const float x4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // rows past the end are neutral: 0.5 + 0.5 = 1 (pairs), 1 (singlets)
+                    if (4 * q + k < GT) a[u][4 * q + k] = ok ? fmaf(x4[k], w, ef) : (SINGLETS ? 1.f : 0.5f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < WAVES; ++u) {
+            int c = 0;
+#pragma unroll
+            for (int i = 0; i < GT; ++i) {
+                if constexpr (SINGLETS) {
+                    prod[i] = __fmul_rn(prod[i], a[u][i]);
+                } else {
+#pragma unroll
+                    for (int j = i; j < GT; ++j, ++c) prod[c] = __fmul_rn(prod[c], __fadd_rn(a[u][i], a[u][j]));
+                }
+            }
+        }
+        since_flush += WAVES;
+        if (since_flush >= FLUSH_ROWS) {  // lane-local row count: uniform across the warp's active lanes
+            since_flush = 0;
+            ++n_flushes;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const unsigned bits = __float_as_uint(prod[c]);
+                esum[c] += (int)(bits >> 23);
+                prod[c] = __uint_as_float((bits & 0x007fffffu) | 0x3f800000u);
+            }
+        }
+    }
+
+    // ---- epilogue: per-lane log2, float64 xor-tree over the lanes, penalties, rounding ------------------------------
+    const int G = p.n_genotypes;
+    const double real_rows = SINGLETS ? 0.0 : (double)(row_hi - row_lo);  // a real row's pair factor carries a 2
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < GT; ++i)
+#pragma unroll
+        for (int j = i; j < (SINGLETS ? i + 1 : GT); ++j, ++c) {
+            double v = (double)(esum[c] - 127 * n_flushes) + (double)wlg2(prod[c]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == (c & 31) && i < G && j < G) {
+                const double sum = v - real_rows;
+                const int64_t col = (i == j) ? i : (int64_t)G + (int64_t)i * G - (int64_t)i * (i + 1) / 2 + (j - i - 1);
+                if (n_seg == 1) {
+                    const float pen = (i == j) ? 0.f : p.doublet_bonus;
+                    float logit = (float)((double)pen + sum * 0.693147180559945309417232);
+                    if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
+                    p.logits[barcode * p.ld_logits + col] = logit;
+                } else {
+                    p.partial[(int64_t)item * p.n_cols + col] = sum;
+                }
+            }
+        }
+}
+
 // ---- work items ---------------------------------------------------------------------------------------------------
 
 __global__ void plan_segments_kernel(const int64_t* __restrict__ offsets, const int32_t* __restrict__ order,
@@ -726,6 +832,7 @@ bool estep_pairs_warp_supported(int G, int flavour) {
     if (flavour != DMX_ESTEP_FAST) return false;
     if (warp_env_int("DMX_PAIRS_WARP", 1) == 0) return false;
     const int nb = (G + 7) / 8;
+    if (G <= 8) return warp_env_int("DMX_PAIRS_SMALL", 1) != 0;   // lane-per-row kernel
     if (nb == 3 || nb == 4 || nb == 5 || nb == 7) return true;  // lane utilisation >= 28 / 32
     return patch_kernel_supported(G);                            // other widths: estep_pairs.cu
 }
@@ -757,7 +864,7 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
     p.table = table;
     p.ld_table = ld_table;
     p.n_genotypes = G;
-    p.doublet_bonus = pair_doublet_bonus(G, doublet_prior);
+    p.doublet_bonus = doublet_prior == 0 ? 0.f : pair_doublet_bonus(G, doublet_prior);
     p.prior = prior_logits;
     p.ld_prior = ld_prior;
     p.logits = logits;
@@ -769,6 +876,20 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
     // 16 factors per product need 16 * -log2(2 (floor + 1e-4)) <= 120 binades; 8 factors are always safe
     const bool long_products = table_floor >= 0.0027f && warp_env_int("DMX_FLUSH_ROWS", 16) == 16;
     const int nb = (G + 7) / 8;
+    if (G <= 8) {
+        // 16 (8) factors in [2 (floor + 1e-4), 2.0002] per product between flushes, as in the tiled kernels; singlet
+        // factors are only >= 1e-4: always 8
+#define DMX_SMALL(GT_)                                                                                        \
+        if (doublet_prior == 0) estep_pairs_small_kernel<GT_, 8, true><<<(unsigned)n_items, 32, 0, stream>>>(p);  \
+        else if (long_products) estep_pairs_small_kernel<GT_, 16, false><<<(unsigned)n_items, 32, 0, stream>>>(p); \
+        else estep_pairs_small_kernel<GT_, 8, false><<<(unsigned)n_items, 32, 0, stream>>>(p)
+        if (G <= 2) { DMX_SMALL(2); }
+        else if (G <= 4) { DMX_SMALL(4); }
+        else { DMX_SMALL(8); }
+#undef DMX_SMALL
+        DMX_LAUNCH_CHECK();
+        return 0;
+    }
     const int variant = warp_env_int("DMX_WARP_VARIANT", 0);  // experiments: exponent packing / occupancy target
 #define DMX_WARP(NB_, SR_, ESM_, REGS_, PF_)                                                                   \
     return long_products ? launch_warp_variant<NB_, 16, SR_, ESM_, REGS_, PF_>(p, n_items, stream)            \

@@ -292,6 +292,12 @@ def test_shapes_vs_oracle(D, shape, flavour):
 # widths served by the warp-per-item pair kernel (8 x 8 register tiles: 3, 4, 5 and 7 blocks of 8 genotypes), with
 # segment lengths that cut most barcodes into several work items, against the oracle and against the CTA kernel
 WARP_SHAPES = [
+    # lane-per-row kernel (G <= 8)
+    dict(n_genotypes=1, n_snps=200, n_barcodes=40, rows_per_barcode=90, seed=40),
+    dict(n_genotypes=3, n_snps=400, n_barcodes=80, rows_per_barcode=300, seed=41, empty_barcode_fraction=0.2),
+    dict(n_genotypes=4, n_snps=800, n_barcodes=150, rows_per_barcode=700, seed=42),
+    dict(n_genotypes=7, n_snps=500, n_barcodes=70, rows_per_barcode=45, seed=43, shuffle_variants=True),
+    dict(n_genotypes=8, n_snps=900, n_barcodes=90, rows_per_barcode=400, seed=44),
     dict(n_genotypes=17, n_snps=500, n_barcodes=60, rows_per_barcode=150, seed=31),
     dict(n_genotypes=24, n_snps=900, n_barcodes=50, rows_per_barcode=260, seed=32, empty_barcode_fraction=0.2),
     dict(n_genotypes=30, n_snps=2500, n_barcodes=120, rows_per_barcode=700, seed=33, shuffle_variants=True),
@@ -321,6 +327,11 @@ def test_warp_pair_kernel_widths_and_segments(D, native_lib, shape, seg_rows):
         D.estep_segment_rows = seg_rows
         gl, gp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.35)
         check_logits_and_posteriors(f'warp/G{G}/seg{seg_rows}', gl.values, ol.values, gp.values, op.values)
+        if G <= 8:  # the lane-per-row kernel also serves the singlet-only E-step
+            assert native_lib.dmx_estep_plan_supported(G, 0.0, 1) == 1
+            sl, sp = O.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.)
+            tl, tp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.)
+            check_logits_and_posteriors(f'warp/G{G}/seg{seg_rows}/dp0', tl.values, sl.values, tp.values, sp.values)
         # the plan itself: every barcode appears in ceil(rows / seg_rows) consecutive items (at least one)
         pack = D._pack_device(ds.calls, ds.genotypes, ds.barcode_handler.n_barcodes, add_data_prior=False)
         seg_prefix, item_slot, n_items, _ = D._estep_plan(pack, 0.35)
