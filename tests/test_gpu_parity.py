@@ -298,6 +298,10 @@ WARP_SHAPES = [
     dict(n_genotypes=4, n_snps=800, n_barcodes=150, rows_per_barcode=700, seed=42),
     dict(n_genotypes=7, n_snps=500, n_barcodes=70, rows_per_barcode=45, seed=43, shuffle_variants=True),
     dict(n_genotypes=8, n_snps=900, n_barcodes=90, rows_per_barcode=400, seed=44),
+    # warp kernel with 3 tiles x 10 row groups (9 <= G <= 16)
+    dict(n_genotypes=9, n_snps=700, n_barcodes=60, rows_per_barcode=250, seed=45, empty_barcode_fraction=0.2),
+    dict(n_genotypes=13, n_snps=900, n_barcodes=70, rows_per_barcode=500, seed=46, shuffle_variants=True),
+    dict(n_genotypes=16, n_snps=1200, n_barcodes=100, rows_per_barcode=800, seed=47),
     dict(n_genotypes=17, n_snps=500, n_barcodes=60, rows_per_barcode=150, seed=31),
     dict(n_genotypes=24, n_snps=900, n_barcodes=50, rows_per_barcode=260, seed=32, empty_barcode_fraction=0.2),
     dict(n_genotypes=30, n_snps=2500, n_barcodes=120, rows_per_barcode=700, seed=33, shuffle_variants=True),
