@@ -12,6 +12,8 @@
 // than HEAVY_ROWS rows (expression skew: a few variants are seen in most barcodes) are processed by a second launch
 // in which all warps of a CTA share one variant.  No atomics anywhere.
 // HBM / L2-gather bound: 8 bytes of row records + 4G gathered bytes per row, 4G bytes written per variant.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dmx {
@@ -524,6 +526,13 @@ static int launch_mstep(cudaStream_t stream, const int64_t* offsets, const int32
         return quads == LPR * SLOTS ? launch_pair<LPR, SLOTS, SQUARE, true>(DMX_ARGS)                      \
                                     : launch_pair<LPR, SLOTS, SQUARE, false>(DMX_ARGS);                    \
     }
+    // few genotypes: fewer lanes per row, more rows (light tier: more variants) side by side in a warp -- with 8 lanes
+    // per row a 4-genotype M-step kept 7 of 8 lanes idle.  DMX_MSTEP_MIN_LPR=8 restores that for comparison.
+    const char* min_lpr_env = getenv("DMX_MSTEP_MIN_LPR");
+    const int min_lpr = (min_lpr_env && *min_lpr_env) ? atoi(min_lpr_env) : 1;
+    if (quads <= 1 && min_lpr <= 1) DMX_SHAPE(1, 1);
+    if (quads <= 2 && min_lpr <= 2) DMX_SHAPE(2, 1);
+    if (quads <= 4 && min_lpr <= 4) DMX_SHAPE(4, 1);
     if (quads <= 8) DMX_SHAPE(8, 1);
     if (quads <= 16) DMX_SHAPE(16, 1);
     if (quads <= 32) DMX_SHAPE(32, 1);

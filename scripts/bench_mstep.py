@@ -10,7 +10,8 @@ from demuxalot_b200.synthetic import make_config
 
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 workload = sys.argv[2] if len(sys.argv) > 2 else 'pbmc_32'
-ds = make_config(workload, scale=scale)
+overrides = {kv.split('=')[0]: int(kv.split('=')[1]) for kv in sys.argv[3:]}
+ds = make_config(workload, scale=scale, **overrides)
 pack = Demultiplexer._pack_device(ds.calls, ds.genotypes, ds.barcode_handler.n_barcodes, add_data_prior=True)
 table = Demultiplexer._probs_table(pack, None, 0.01)
 _, _, singlets = Demultiplexer._e_step(pack, table, 0.35, want_logits=False, want_post=False, want_singlets=True)

@@ -182,7 +182,7 @@ def test_m_step_bit_exact_given_identical_posteriors(D):
         D.contribution_power = 2.
 
 
-@pytest.mark.parametrize('G', [5, 32, 64, 200])
+@pytest.mark.parametrize('G', [3, 5, 12, 32, 64, 200])
 def test_planned_m_step_tiers_vs_oracle_and_unplanned(D, G):
     """Light / medium / heavy tiers of the planned M-step (few SNPs and many barcodes give variants with more than
     4096 rows) against np.bincount's float64 sums and against the one-warp-per-variant schedule."""
