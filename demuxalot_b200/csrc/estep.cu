@@ -241,7 +241,10 @@ static int launch_singlets(unsigned grid, cudaStream_t stream, const int64_t* of
 #define DMX_SINGLETS(LPR, SLOTS)                                                                                  \
     estep_singlets_kernel<FLAVOUR, LPR, SLOTS><<<grid, 128, 0, stream>>>(offsets, order, variant, e, table, ld_table, \
                                                                          G, prior, ld_prior, logits, ld_logits)
-    if (quads <= 8) DMX_SINGLETS(8, 1);
+    if (quads <= 1) DMX_SINGLETS(1, 1);  // few genotypes: fewer lanes per row, more rows side by side in a warp
+    else if (quads <= 2) DMX_SINGLETS(2, 1);
+    else if (quads <= 4) DMX_SINGLETS(4, 1);
+    else if (quads <= 8) DMX_SINGLETS(8, 1);
     else if (quads <= 16) DMX_SINGLETS(16, 1);
     else if (quads <= 32) DMX_SINGLETS(32, 1);
     else if (quads <= 64) DMX_SINGLETS(32, 2);
