@@ -136,7 +136,7 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order /* dm
               or NULL, NULL, 0, 0 */, void* stream);
 
 /* Work items of the warp-per-item E-step kernels (FAST flavour; dmx_estep_plan_supported tells whether a
- * configuration is served by them: doublet_prior != 0 with 1..40, 49..56 or most of 73..256 genotypes, and
+ * configuration is served by them: doublet_prior != 0 with 1..40, 49..56 or 65..256 genotypes, and
  * doublet_prior == 0 with up to 8 genotypes): a
  * barcode with more than seg_rows rows is cut into ceil(rows / seg_rows) segments so that no single warp carries a
  * deep barcode alone; the segments' float64 partial sums are added in segment order (deterministic).  Outputs, by

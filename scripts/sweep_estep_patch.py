@@ -14,14 +14,14 @@ widths = [int(a) for a in sys.argv[1:]] or [200, 104]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device='cuda')
 for G in widths:
     C = G * (G + 1) // 2
-    n_barcodes = max(300, int(2.0e11 / C / 3000))  # ~2e11 updates per E-step: thousands of work items
+    n_barcodes = max(300, int(float(os.environ.get('SWEEP_UPDATES', '2.0e11')) / C / 3000))  # thousands of work items
     ds = make_dataset(n_genotypes=G, n_snps=100_000, n_barcodes=n_barcodes, rows_per_barcode=3000, seed=20260003,
                       tiny_error_fraction=0.0)
     pack = Demultiplexer._pack_device(ds.calls, ds.genotypes, n_barcodes, add_data_prior=False)
     table = Demultiplexer._probs_table(pack, None, 0.01)
     print(f'G={G} C={C} B={n_barcodes} R={pack.n_rows} V={pack.n_variants} updates={pack.n_rows * C:.3e}', flush=True)
     base = None
-    for label, env, seg in (('CTA kernel', dict(DMX_PAIRS_PATCH=0), 4096), ('patch kernel', dict(DMX_PAIRS_PATCH=1), 4096),
+    for label, env, seg in (('CTA kernel', dict(DMX_PAIRS_PATCH=0), 4096), ('patch kernel', dict(DMX_PAIRS_PATCH=1, DMX_PAIRS_PATCH_MIN_EFF=os.environ.get('SWEEP_MIN_EFF', '80')), 4096),
                             ('patch kernel seg 2048', dict(DMX_PAIRS_PATCH=1), 2048)):
         os.environ.update({k: str(v) for k, v in env.items()})
         Demultiplexer.estep_segment_rows = seg

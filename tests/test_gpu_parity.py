@@ -308,6 +308,7 @@ WARP_SHAPES = [
     dict(n_genotypes=37, n_snps=1200, n_barcodes=40, rows_per_barcode=180, seed=34),
     dict(n_genotypes=53, n_snps=1500, n_barcodes=30, rows_per_barcode=120, seed=35),
     # patch kernel (a warp per 32-tile patch of the triangle): 10, 18, 21 and 25 blocks of 8 genotypes
+    dict(n_genotypes=70, n_snps=1000, n_barcodes=24, rows_per_barcode=120, seed=48),
     dict(n_genotypes=77, n_snps=1200, n_barcodes=24, rows_per_barcode=150, seed=39),
     dict(n_genotypes=140, n_snps=1200, n_barcodes=20, rows_per_barcode=150, seed=36),
     dict(n_genotypes=165, n_snps=900, n_barcodes=16, rows_per_barcode=90, seed=37, empty_barcode_fraction=0.2),
