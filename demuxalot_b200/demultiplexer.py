@@ -15,6 +15,7 @@ Stage map (reference lines -> ABI call):
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import threading
@@ -74,6 +75,7 @@ def _upload_async(array: np.ndarray, device, copy_stream):
 
 
 _CB_STAGING: Dict[int, dict] = {}
+_CB_STAGING_LOCK = threading.Lock()  # one packing call at a time fills and uploads the per-device staging buffer
 
 
 def _cb_staging(device, n_int32: int) -> dict:
@@ -262,50 +264,52 @@ class Demultiplexer:
             gather = cls.host_gather_threads > 0 and len(parts) > 0
             staging = ready_flags = worker = None
             molecule_arrays = [_as_dtype(c.molecules[:c.n_molecules], MOLECULE_DTYPE) for _cid, c in parts]
-            if gather:
-                n_mols = [c.n_molecules for _cid, c in parts]
-                staging = _cb_staging(dev, sum(n_mols))
-                if staging['last_read'] is not None:
-                    staging['last_read'].synchronize()  # the previous call's upload out of this buffer is done
-                ready_flags = [threading.Event() for _ in parts]
-                base_ptr, n_threads = staging['buffer'].data_ptr(), int(cls.host_gather_threads)
+            # one packing call at a time fills the per-device staging buffer and queues the uploads out of it
+            with (_CB_STAGING_LOCK if gather else contextlib.nullcontext()):
+                if gather:
+                    n_mols = [c.n_molecules for _cid, c in parts]
+                    staging = _cb_staging(dev, sum(n_mols))
+                    if staging['last_read'] is not None:
+                        staging['last_read'].synchronize()  # the previous call's upload out of this buffer is done
+                    ready_flags = [threading.Event() for _ in parts]
+                    base_ptr, n_threads = staging['buffer'].data_ptr(), int(cls.host_gather_threads)
 
-                def gather_all():  # ctypes releases the GIL: runs beside the upload submissions below
+                    def gather_all():  # ctypes releases the GIL: runs beside the upload submissions below
+                        offset = 0
+                        for k, mols in enumerate(molecule_arrays):
+                            rc = -1  # whatever happens the flag is set, so the consumer below never waits for ever
+                            try:
+                                rc = lib.dmx_host_gather_cb(mols.ctypes.data, len(mols), base_ptr + 4 * offset, n_threads)
+                            finally:
+                                ready_flags[k].rc = rc
+                                ready_flags[k].set()
+                            offset += len(mols)
+
+                    worker = threading.Thread(target=gather_all, daemon=True)
+                    worker.start()
+                uploads = []
+                for (cid, calls), molecules in zip(parts, molecule_arrays):
+                    snp_calls = _as_dtype(calls.snp_calls[:calls.n_snp_calls], SNP_CALL_DTYPE)
+                    d_calls, ready = _upload_async(snp_calls, dev, copy_stream)
+                    d_mols = None
+                    if not gather:
+                        d_mols, ready = _upload_async(molecules, dev, copy_stream)
+                    uploads.append([cid, calls, d_calls, d_mols, ready])
+                if gather:  # the compact columns follow the call records on the wire, in the order the gathers finish
                     offset = 0
-                    for k, mols in enumerate(molecule_arrays):
-                        rc = -1  # whatever happens the flag is set, so the consumer below never waits for ever
-                        try:
-                            rc = lib.dmx_host_gather_cb(mols.ctypes.data, len(mols), base_ptr + 4 * offset, n_threads)
-                        finally:
-                            ready_flags[k].rc = rc
-                            ready_flags[k].set()
-                        offset += len(mols)
-
-                worker = threading.Thread(target=gather_all, daemon=True)
-                worker.start()
-            uploads = []
-            for (cid, calls), molecules in zip(parts, molecule_arrays):
-                snp_calls = _as_dtype(calls.snp_calls[:calls.n_snp_calls], SNP_CALL_DTYPE)
-                d_calls, ready = _upload_async(snp_calls, dev, copy_stream)
-                d_mols = None
-                if not gather:
-                    d_mols, ready = _upload_async(molecules, dev, copy_stream)
-                uploads.append([cid, calls, d_calls, d_mols, ready])
-            if gather:  # the compact columns follow the call records on the wire, in the order the gathers finish
-                offset = 0
-                for k, entry in enumerate(uploads):
-                    ready_flags[k].wait()
-                    _native.check(ready_flags[k].rc, 'dmx_host_gather_cb')
-                    n = entry[1].n_molecules
-                    with torch.cuda.stream(copy_stream):
-                        d_cb = staging['buffer'][offset:offset + n].to(dev, non_blocking=True)
-                        event = torch.cuda.Event()
-                        event.record(copy_stream)
-                    d_cb.record_stream(main)
-                    entry[3], entry[4] = d_cb, event
-                    staging['last_read'] = event
-                    offset += n
-                worker.join()
+                    for k, entry in enumerate(uploads):
+                        ready_flags[k].wait()
+                        _native.check(ready_flags[k].rc, 'dmx_host_gather_cb')
+                        n = entry[1].n_molecules
+                        with torch.cuda.stream(copy_stream):
+                            d_cb = staging['buffer'][offset:offset + n].to(dev, non_blocking=True)
+                            event = torch.cuda.Event()
+                            event.record(copy_stream)
+                        d_cb.record_stream(main)
+                        entry[3], entry[4] = d_cb, event
+                        staging['last_read'] = event
+                        offset += n
+                    worker.join()
             if raw.size:
                 raw_dev, raw_ready = _upload_async(raw, dev, copy_stream)
             else:

@@ -41,6 +41,23 @@ def test_abi_library_exports_every_declared_symbol(native_lib):
     assert native_lib.dmx_estep_plan_supported(4, 0.0, 1) and not native_lib.dmx_estep_plan_supported(9, 0.0, 1)
 
 
+def test_host_gather_of_the_barcode_column(native_lib):
+    """dmx_host_gather_cb is a host function (no GPU needed): the compressed_cb column of packed molecule records."""
+    import ctypes as C
+    from demuxalot_b200.calls import MOLECULE_DTYPE
+    rng = np.random.default_rng(0)
+    for n, threads in ((0, 4), (1, 1), (70_001, 1), (300_000, 7), (300_000, 64)):
+        mols = np.zeros(n, dtype=MOLECULE_DTYPE)
+        assert mols.dtype.itemsize == 12
+        mols['compressed_cb'] = rng.integers(-5, 2 ** 31 - 1, size=n)
+        mols['compressed_ub'] = rng.integers(0, 2 ** 31 - 1, size=n)
+        mols['p_group_misaligned'] = rng.random(n)
+        out = np.full(n + 3, -77, dtype=np.int32)
+        rc = native_lib.dmx_host_gather_cb(C.c_void_p(mols.ctypes.data), n, C.c_void_p(out.ctypes.data), threads)
+        assert rc == 0
+        assert np.array_equal(out[:n], mols['compressed_cb']) and (out[n:] == -77).all()
+
+
 def test_product_path_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
