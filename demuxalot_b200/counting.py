@@ -167,6 +167,9 @@ def native_io():
             for name in ('dmxio_n_molecules', 'dmxio_n_calls', 'dmxio_n_reads_seen'):
                 getattr(lib, name).restype = C.c_int64
                 getattr(lib, name).argtypes = [C.c_void_p]
+            lib.dmxio_count_coverage.restype = C.c_int
+            lib.dmxio_count_coverage.argtypes = [C.c_char_p, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, C.c_char_p,
+                                                 C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
             lib.dmxio_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             lib.dmxio_copy.restype = None
             lib.dmxio_free.argtypes = [C.c_void_p]
@@ -233,6 +236,30 @@ def _count_region_native(lib, path: str, chromosome: str, positions: np.ndarray,
     finally:
         lib.dmxio_free(handle)
     return out
+
+
+def count_coverage_native(path, chromosome: str, start: int, stop: int, parse_read: Callable,
+                          quality_threshold: int = 15) -> Optional[np.ndarray]:
+    """int32 [4, stop - start] coverage of reads passing a built-in read filter, by the native loop; None when the
+    filter is a custom callback or libdemux_io.so is not built (the caller then walks the reads in Python)."""
+    lib, params = native_io(), _NATIVE_FILTERS.get(parse_read)
+    if lib is None or params is None:
+        return None
+    info = _bam_info(path)
+    ref_id = info['names'].index(chromosome)
+    voffset = info['first_voffset']
+    if info['bai'] is not None:
+        from_index = region_start_voffset(info['bai'][ref_id], start)
+        voffset = from_index if from_index is not None else voffset
+    counts = np.zeros((4, max(int(stop) - int(start), 0)), dtype=np.int32)
+    if counts.size:
+        rc = lib.dmxio_count_coverage(str(path).encode(), ref_id, voffset, int(start), int(stop),
+                                      params['umi_tag'].encode(), params['nhits_tag'].encode(),
+                                      params['score_tag'].encode(), params['score_diff_max'], params['mapq_threshold'],
+                                      int(quality_threshold), counts.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f'native count_coverage failed: {lib.dmxio_last_error().decode()}')
+    return counts
 
 
 def count_region(bamfile, chromosome: str, positions: np.ndarray, barcode_handler: BarcodeHandler,

@@ -498,6 +498,75 @@ dmxio_result* dmxio_count_region(const char* bam_path, int32_t ref_id, uint64_t 
     }
 }
 
+int dmxio_count_coverage(const char* bam_path, int32_t ref_id, uint64_t start_voffset, int64_t start, int64_t stop,
+                         const char* umi_tag, const char* nhits_tag, const char* score_tag, int32_t score_diff_max,
+                         int32_t mapq_threshold, int32_t quality_threshold, int32_t* counts /* [4, stop - start] */) {
+    try {
+        const bool check_nhits = nhits_tag && nhits_tag[0];
+        const int64_t width = stop - start;
+        Bgzf in(bam_path);
+        in.seek(start_voffset);
+        Read read;
+        std::vector<uint8_t> scratch;
+        std::string text;
+        while (next_read(in, read, scratch)) {
+            if (read.ref_id != ref_id) {
+                if (read.ref_id > ref_id || read.ref_id < 0) break;
+                continue;
+            }
+            if (read.pos >= stop) break;
+            if (read.flag & 4) continue;
+            if ((int64_t)read.end <= start) continue;
+            // read filter: the built-in parse_read accepts the read (cellranger_specific.py / BDRhapsody_specific.py)
+            int64_t score = 0, nhits = 0;
+            if (!read.find_tag(score_tag, &score, nullptr)) throw Fail{std::string("read without ") + score_tag + " tag"};
+            if (score <= (int64_t)read.l_seq - score_diff_max) continue;
+            if (check_nhits) {
+                if (!read.find_tag(nhits_tag, &nhits, nullptr)) throw Fail{std::string("read without ") + nhits_tag + " tag"};
+                if (nhits > 1) continue;
+            }
+            if (!read.find_tag(umi_tag, nullptr, &text)) continue;
+            if ((int)read.mapq < mapq_threshold) continue;
+            if (read.l_seq == 0) continue;
+            // aligned bases only (M, =, X); I / S advance the read, D / N the reference, H / P neither
+            int64_t qpos = 0, rpos = read.pos;
+            for (uint32_t c : read.cigar) {
+                const unsigned op = c & 0xF;
+                const int64_t len = c >> 4;
+                if (op == 0 || op == 7 || op == 8) {
+                    const int64_t lo = std::max<int64_t>(rpos, start), hi = std::min<int64_t>(rpos + len, stop);
+                    for (int64_t r = lo; r < hi; ++r) {
+                        const int64_t q = qpos + (r - rpos);
+                        if (quality_threshold && (int)read.qual[(size_t)q] < quality_threshold) continue;
+                        int code;
+                        switch (read.base((int)q)) {
+                            case 'A': code = 0; break;
+                            case 'C': code = 1; break;
+                            case 'G': code = 2; break;
+                            case 'T': code = 3; break;
+                            default: continue;
+                        }
+                        ++counts[code * width + (r - start)];
+                    }
+                    qpos += len;
+                    rpos += len;
+                } else if (op == 1 || op == 4) {
+                    qpos += len;
+                } else if (op == 2 || op == 3) {
+                    rpos += len;
+                }
+            }
+        }
+        return 0;
+    } catch (const Fail& f) {
+        g_error = f.what;
+        return -1;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return -1;
+    }
+}
+
 int64_t dmxio_n_molecules(const dmxio_result* r) { return r->n_molecules; }
 int64_t dmxio_n_calls(const dmxio_result* r) { return r->n_calls; }
 int64_t dmxio_n_reads_seen(const dmxio_result* r) { return r->n_reads_seen; }

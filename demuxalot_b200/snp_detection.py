@@ -20,7 +20,7 @@ import pandas as pd
 from .bam import BamFile
 from .barcodes import BarcodeHandler
 from .calls import CompressedSNPCalls
-from .counting import _open_cached, count_snps, parse_read as cellranger_parse_read
+from .counting import _open_cached, count_coverage_native, count_snps, parse_read as cellranger_parse_read
 from .genotype_store import ProbabilisticGenotypes
 
 _BASE_CODE = np.full(256, -1, dtype=np.int8)
@@ -108,8 +108,11 @@ def detect_snps_for_chromosome(bamfile_path, chromosome, start, stop, sorted_don
     coverage = 0
     bamfiles = [bamfile_path] if isinstance(bamfile_path, (str, Path)) else list(bamfile_path.values())
     for filename in bamfiles:
-        coverage = coverage + count_coverage(_open_cached(filename), chromosome, start, stop,
-                                             read_callback=lambda read: parse_read(read) is not None)
+        native = count_coverage_native(filename, chromosome, start, stop, parse_read)  # built-in read filters only
+        if native is None:
+            native = count_coverage(_open_cached(filename), chromosome, start, stop,
+                                    read_callback=lambda read: parse_read(read) is not None)
+        coverage = coverage + native
     total = coverage.sum(axis=0)
     *_, alt, ref = np.sort(coverage, axis=0)
     is_candidate = (ref + alt) > minimum_coverage

@@ -37,6 +37,15 @@ dmxio_result* dmxio_count_region(const char* bam_path, int32_t ref_id, uint64_t 
                                  const char* umi_tag, const char* nhits_tag, const char* score_tag,
                                  int32_t score_diff_max, int32_t mapq_threshold, double p_misaligned_default);
 
+/* Per-base coverage of [start, stop) of one reference: counts[b * (stop - start) + (pos - start)] += 1 for every
+ * aligned (M / = / X) base b in A, C, G, T with base quality >= quality_threshold of every mapped read that passes
+ * the built-in read filter -- what `np.asarray(pysam.AlignmentFile.count_coverage(..., read_callback=lambda r:
+ * parse_read(r) is not None))` returns for `detect_snps_for_chromosome` (snp_detection.py:33-42).  `counts` is
+ * caller-owned int32 [4, stop - start], zero-initialised.  Returns 0, or -1 on error (dmxio_last_error()). */
+int dmxio_count_coverage(const char* bam_path, int32_t ref_id, uint64_t start_voffset, int64_t start, int64_t stop,
+                         const char* umi_tag, const char* nhits_tag, const char* score_tag, int32_t score_diff_max,
+                         int32_t mapq_threshold, int32_t quality_threshold, int32_t* counts);
+
 int64_t dmxio_n_molecules(const dmxio_result* r);
 int64_t dmxio_n_calls(const dmxio_result* r);
 int64_t dmxio_n_reads_seen(const dmxio_result* r);

@@ -77,12 +77,17 @@ def test_count_coverage_against_a_plain_loop(tmp_path):
                                          tags={'NH': 1 + int(k % 7 == 0), 'AS': n_query - 1, 'UB': 'ACGT', 'CB': 'X-1'})))
     reads.sort(key=lambda t: t[0])
     write_bam(path, [('chr1', 1000)], [r for _s, r in reads])
+    from demuxalot_b200.counting import count_coverage_native, native_io
     for start, stop in ((0, 1000), (137, 611)):
         mine = snp_detection.count_coverage(_open_cached(path), 'chr1', start, stop, lambda r: parse_read(r) is not None)
         with pysam_shim.AlignmentFile(str(path)) as f:
             want = np.asarray(f.count_coverage('chr1', start=start, stop=stop,
                                                read_callback=lambda r: parse_read(r) is not None), dtype='int32')
         assert mine.dtype == np.int32 and np.array_equal(mine, want) and mine.sum() > 1000
+        if native_io() is not None:  # the native loop (built-in read filters) gives the same matrix
+            fast = count_coverage_native(path, 'chr1', start, stop, parse_read)
+            assert fast.dtype == np.int32 and np.array_equal(fast, want)
+            assert count_coverage_native(path, 'chr1', start, stop, lambda r: parse_read(r)) is None  # custom callback
 
 
 @pytest.mark.skipif(not reference_available(), reason='/root/reference not mounted')
