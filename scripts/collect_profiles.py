@@ -117,7 +117,8 @@ if (SRC / 'launches.csv').exists():
     launch_shares(SRC / 'launches.csv')
 for rep, name in (('prof_estep_full.ncu-rep', 'estep_pairs'), ('prof_aux.ncu-rep', 'mstep_singlets_table_softmax'),
                   ('prof_patch.ncu-rep', 'estep_pairs_patch_g200'), ('prof_singlets.ncu-rep', 'estep_singlets'),
-                  ('r01b_mstep_light.ncu-rep', 'mstep_light_tier')):
+                  ('r01b_mstep_light.ncu-rep', 'mstep_light_tier'), ('prof_mstep_tiers.ncu-rep', 'mstep_tiers'),
+                  ('prof_small.ncu-rep', 'estep_lane_per_row_g4')):
     if (SRC / rep).exists():
         traffic = summarise_report(SRC / rep, name)
         if name == 'estep_pairs' and traffic:
