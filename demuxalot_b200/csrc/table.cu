@@ -5,6 +5,8 @@
 // variants in ascending variant id, which is the order np.bincount adds them in, so results are bit-exact.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace dmx {
 
 // numpy's float32 pairwise summation (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum) as used by
@@ -112,12 +114,12 @@ __global__ void probs_table_kernel(const float* __restrict__ betas, int64_t ld_b
 }
 
 // Vector flavour for G % 4 == 0 (no padding columns): a thread owns 4 consecutive columns of one SNP and keeps the
-// rows of up to TABLE_MAXV variants in registers, so each element is read once with 128-bit loads and four times the
+// rows of up to TABLE_MAXV variants in registers, so each element is read once with 128-bit loads and several times the
 // bytes are in flight per thread (the scalar kernel reached only 29 % of the HBM peak: one 4-byte load per thread at
 // the end of a dependent offsets -> variant -> betas chain).  Same arithmetic, same summation order: bit-exact.
-constexpr int TABLE_MAXV = 4;
-
-__global__ void __launch_bounds__(256) probs_table_vec4_kernel(
+// TABLE_MAXV / MINB (resident CTAs asked of the compiler) are template knobs so that DMX_TABLE_* can sweep them.
+template <int TABLE_MAXV, int MINB>
+__global__ void __launch_bounds__(256, MINB) probs_table_vec4_kernel(
     const float* __restrict__ betas, int64_t ld_betas, const float* __restrict__ addition, int64_t ld_add, int quads,
     const int32_t* __restrict__ snp_offsets, const int32_t* __restrict__ snp_variants, int64_t n_snps, float clip_lo,
     float clip_hi, float* __restrict__ table, int64_t ld_table) {
@@ -173,10 +175,15 @@ __global__ void __launch_bounds__(256) probs_table_vec4_kernel(
     }
 }
 
-static inline int grid_1d(int64_t n, int threads) {
+static inline int grid_1d(int64_t n, int threads, int ctas_per_sm = 32) {
     int64_t blocks = ceil_div(n > 0 ? n : 1, threads);
-    const int64_t cap = (int64_t)sm_count() * 32;
+    const int64_t cap = ctas_per_sm > 0 ? (int64_t)sm_count() * ctas_per_sm : (int64_t)0x7fffffff;
     return (int)(blocks < cap ? blocks : cap);
+}
+
+static inline int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
 }
 
 }  // namespace dmx
@@ -215,9 +222,20 @@ int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addi
                       ((uintptr_t)table & 15) == 0 && (!addition || (ld_addition % 4 == 0 && ((uintptr_t)addition & 15) == 0));
     if (vec4) {
         const int quads = n_genotypes / 4;
-        probs_table_vec4_kernel<<<grid_1d(n_snps * quads, threads), threads, 0, (cudaStream_t)stream_>>>(
-            betas, ld_betas, addition, ld_addition, quads, snp_offsets, snp_variants, n_snps, clip_lo, clip_hi, table,
-            ld_table);
+        // Defaults from scripts/sweep_table.py (profiles/r01_sweep_table.log): 2 rows in registers (bi-allelic SNPs,
+        // anything wider takes the two-pass loop) and 5 resident CTAs (48 registers, 32 bytes of spills) run 25-28 % faster
+        // than 4 rows at 68 registers; 6 CTAs spill 156 bytes and lose.  Knobs: rows in registers, resident CTAs, grid cap in CTAs per SM.
+        const int maxv = env_int("DMX_TABLE_MAXV", 2), minb = env_int("DMX_TABLE_MINB", 5);
+        const int grid = grid_1d(n_snps * quads, threads, env_int("DMX_TABLE_CAP", 32));
+#define DMX_TABLE_LAUNCH(MAXV, MINB)                                                                                 \
+    probs_table_vec4_kernel<MAXV, MINB><<<grid, threads, 0, (cudaStream_t)stream_>>>(                                \
+        betas, ld_betas, addition, ld_addition, quads, snp_offsets, snp_variants, n_snps, clip_lo, clip_hi, table,   \
+        ld_table)
+        if (maxv == 2 && minb >= 5) DMX_TABLE_LAUNCH(2, 5);
+        else if (maxv == 2) DMX_TABLE_LAUNCH(2, 4);
+        else if (minb >= 4) DMX_TABLE_LAUNCH(4, 4);
+        else DMX_TABLE_LAUNCH(4, 1);
+#undef DMX_TABLE_LAUNCH
         DMX_LAUNCH_CHECK();
         return 0;
     }
