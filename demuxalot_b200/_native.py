@@ -42,11 +42,18 @@ SIGNATURES = {
     'dmx_mstep_plan': (C.c_int, [_ptr, _i64, _i64, _ptr, _i64, C.POINTER(_i64), _ptr]),
     'dmx_mstep_planned': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _i64, _i64,
                                     _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr]),
+    'dmx_snp_groups_workspace_bytes': (_i64, [_i64]),
+    'dmx_build_snp_groups': (C.c_int, [_ptr, _ptr, _ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _ptr, _i64, _ptr, _ptr, _ptr,
+                                       _ptr, C.POINTER(_i64), C.POINTER(_i64), _ptr]),
+    'dmx_snp_logits_workspace_bytes': (_i64, [_i64, _i32]),
+    'dmx_snp_logits': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f64, _f64, _ptr, _i64, _ptr, _i64,
+                                 _ptr]),
+    'dmx_softmax_rows_f64': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     'dmx_round_f64_to_f32': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr]),
 }
 
 ESTEP_EXACT, ESTEP_FAST = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class NativeError(RuntimeError):

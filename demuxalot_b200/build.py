@@ -14,7 +14,8 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / 'csrc'
 LIB_PATH = CSRC / 'libdemux_b200.so'
-SOURCES = ['api.cu', 'builder.cu', 'table.cu', 'estep.cu', 'estep_pairs.cu', 'estep_pairs_warp.cu', 'mstep.cu']
+SOURCES = ['api.cu', 'builder.cu', 'table.cu', 'estep.cu', 'estep_pairs.cu', 'estep_pairs_warp.cu', 'mstep.cu',
+           'snp_aggregate.cu']
 HEADERS = [CSRC / 'common.cuh', CSRC.parent.parent / 'include' / 'demux_b200.h']
 
 HOST_SRC = CSRC.parent / 'csrc_host' / 'bam_counter.cpp'

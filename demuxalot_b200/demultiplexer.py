@@ -12,6 +12,8 @@ Stage map (reference lines -> ABI call):
   _compute_probs_from_betas      demux.py:267-274  -> dmx_probs_from_betas
   compute_barcode_logits + softmax  demux.py:246-265,101,152 -> dmx_estep
   M-step loop                    demux.py:113-118  -> dmx_mstep
+  compute_barcode_logits, aggregate_on_snps=True  demux.py:204-244 -> dmx_build_snp_groups, dmx_snp_logits,
+                                                                      dmx_softmax_rows_f64
 """
 from __future__ import annotations
 
@@ -179,7 +181,9 @@ class Demultiplexer:
     Same static API and class attributes as the reference (demux.py:24-32).
     """
     contribution_power = 2.
-    aggregate_on_snps = False  # the experimental branch (demux.py:204-244) is not part of this path
+    # True selects the reference's experimental per-(barcode, SNP) regularised likelihood (demux.py:204-244): float64
+    # logits / posteriors, no doublet penalties -- quirks of the reference kept as they are (_e_step_aggregated)
+    aggregate_on_snps = False
     compensation_during_computing_barcode_logits = 0.5
 
     # B200-specific knobs (not in the reference)
@@ -587,17 +591,100 @@ class Demultiplexer:
                 pack.n_genotypes, _stream()), 'dmx_round_f64_to_f32')
         return out
 
+    # ------------------------------------------------------------------------------------------------ aggregate_on_snps
+    @classmethod
+    def _snp_groups(cls, pack: DevicePack):
+        """(barcode, SNP) groups of the matched molecule-level calls (demux.py:214-218), built once per pack:
+        (grouped_variant, grouped_e, group_offsets, barcode_group_offsets, n_matched, n_groups)."""
+        cached = pack.__dict__.get('_snp_groups')
+        if cached is None:
+            lib = _native.load()
+            dev = pack.device
+            n = pack.n_calls
+            cap = max(n, 1)
+            grouped_variant = torch.empty(cap, dtype=torch.int32, device=dev)
+            grouped_e = torch.empty(cap, dtype=torch.float32, device=dev)
+            group_offsets = torch.empty(cap + 1, dtype=torch.int64, device=dev)
+            barcode_group_offsets = torch.empty(pack.n_barcodes + 1, dtype=torch.int64, device=dev)
+            ws_bytes = lib.dmx_snp_groups_workspace_bytes(n)
+            if ws_bytes < 0:
+                _native.check(-1, 'dmx_snp_groups_workspace_bytes')
+            workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+            h_matched, h_groups = C.c_int64(0), C.c_int64(0)
+            lo, hi = pack.barcode_range
+            with torch.cuda.device(dev):
+                variant2snp = _to_device(np.ascontiguousarray(pack.variant2snp, dtype=np.int32), dev)
+                _native.check(lib.dmx_build_snp_groups(
+                    pack.call_variant.data_ptr(), pack.call_cb.data_ptr(), pack.call_e.data_ptr(), n,
+                    variant2snp.data_ptr(), pack.n_snps, pack.n_barcodes, lo, hi, workspace.data_ptr(), ws_bytes,
+                    grouped_variant.data_ptr(), grouped_e.data_ptr(), group_offsets.data_ptr(),
+                    barcode_group_offsets.data_ptr(), C.byref(h_matched), C.byref(h_groups), _stream()),
+                    'dmx_build_snp_groups')  # synchronises the stream: the pageable upload above is complete
+            # FeatureLookup takes np.max of the features (utils.py:213): the reference raises on zero matched calls
+            if h_matched.value == 0:
+                raise ValueError('aggregate_on_snps=True needs at least one matched call')
+            cached = pack.__dict__['_snp_groups'] = (grouped_variant, grouped_e, group_offsets, barcode_group_offsets,
+                                                     int(h_matched.value), int(h_groups.value))
+        return cached
+
+    @classmethod
+    def _e_step_aggregated(cls, pack: DevicePack, table: torch.Tensor, doublet_prior: float,
+                           prior_logits: Optional[torch.Tensor] = None, want_post: bool = True,
+                           want_singlets: bool = False, buffers: Optional[dict] = None):
+        """`aggregate_on_snps = True` (demux.py:204-244) + softmax: (float64 logits, float64 posteriors, float32
+        singlet posteriors for the M-step).  The reference feeds its float64 posteriors to the M-step; here they are
+        rounded to float32 first (6e-8 relative on each weight)."""
+        lib = _native.load()
+        dev = pack.device
+        n_cols = n_options(pack.n_genotypes, doublet_prior)
+        buffers = {} if buffers is None else buffers
+        grouped_variant, grouped_e, group_offsets, barcode_group_offsets, _n_matched, _n_groups = cls._snp_groups(pack)
+
+        def buf(name, shape, dtype):
+            t = buffers.get(name)
+            if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+                t = buffers[name] = torch.zeros(shape, dtype=dtype, device=dev)
+            return t
+
+        logits = buf('snp_logits', (pack.n_barcodes, n_cols), torch.float64)
+        post = buf('snp_post', (pack.n_barcodes, n_cols), torch.float64) if want_post else None
+        singlets = buf('singlets', (pack.n_barcodes, cls._table_ld(pack.n_genotypes)), torch.float32) \
+            if want_singlets else None
+        ws_bytes = lib.dmx_snp_logits_workspace_bytes(pack.n_barcodes, n_cols)
+        workspace = buffers.get('snp_ws')
+        if workspace is None or workspace.numel() < ws_bytes:
+            workspace = buffers['snp_ws'] = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(lib.dmx_snp_logits(
+                barcode_group_offsets.data_ptr(), group_offsets.data_ptr(), grouped_variant.data_ptr(),
+                grouped_e.data_ptr(), pack.n_barcodes, table.data_ptr(), table.shape[1], pack.n_genotypes,
+                float(doublet_prior), float(cls.compensation_during_computing_barcode_logits), logits.data_ptr(),
+                n_cols, workspace.data_ptr(), ws_bytes, _stream()), 'dmx_snp_logits')
+            _native.check(lib.dmx_softmax_rows_f64(
+                logits.data_ptr(), n_cols, _native.ptr(prior_logits), n_cols, pack.n_barcodes, n_cols,
+                _native.ptr(post), n_cols, _native.ptr(singlets), cls._table_ld(pack.n_genotypes), pack.n_genotypes,
+                _stream()), 'dmx_softmax_rows_f64')
+        return logits, post, singlets
+
+    @classmethod
+    def _e_step_any(cls, pack, table, doublet_prior, **kwargs):
+        """demux.py:193-202: the class flag picks the likelihood."""
+        if cls.aggregate_on_snps:
+            assert cls.process_group is None, 'aggregate_on_snps=True is a single-GPU path'
+            kwargs.pop('want_logits', None)  # the float64 logits buffer is always filled
+            return cls._e_step_aggregated(pack, table, doublet_prior, **kwargs)
+        return cls._e_step(pack, table, doublet_prior, **kwargs)
+
     # ------------------------------------------------------------------------------------------------ public API
     @classmethod
     def predict_posteriors(cls, chromosome2compressed_snp_calls, genotypes, barcode_handler,
                            p_genotype_clip=0.01, doublet_prior=0.35):
         """One E-step with the given genotypes (demux.py:120-156): returns (logits_df, probs_df)."""
-        assert not cls.aggregate_on_snps, 'aggregate_on_snps=True is not implemented on the CUDA path'
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
                                 add_data_prior=False)
         table = cls._probs_table(pack, None, p_genotype_clip)
         table_is_finite = torch.isfinite(table).all()  # demux.py:135; read back together with the results
-        logits, post, _ = cls._e_step(pack, table, doublet_prior)
+        logits, post, _ = cls._e_step_any(pack, table, doublet_prior)
         extras = [table_is_finite] + ([pack.betas_min] if pack.betas_min is not None else [])
         logits_np, post_np, finite, *betas_min = _to_host(logits, post, *extras)
         pack.check(*betas_min)  # demux.py:374 (the reference asserts before computing; the result is the same)
@@ -626,7 +713,8 @@ class Demultiplexer:
         device->host copy of the [B, C] matrices per iteration.  `learn_genotypes` avoids those copies.
         """
         assert 0 <= doublet_prior < 1
-        assert not cls.aggregate_on_snps, 'aggregate_on_snps=True is not implemented on the CUDA path'
+        assert not (cls.aggregate_on_snps and cls.process_group is not None), \
+            'aggregate_on_snps=True is a single-GPU path'
         n_cols = n_options(genotypes.n_genotypes, doublet_prior)
         if barcode_prior_logits is not None:
             assert barcode_prior_logits.shape == (barcode_handler.n_barcodes, n_cols), 'wrong shape of priors'
@@ -640,7 +728,7 @@ class Demultiplexer:
         addition = torch.zeros_like(pack.betas)
         for iteration in range(n_iterations):
             table = cls._probs_table(pack, addition, p_genotype_clip)
-            logits, post, singlets = cls._e_step(
+            logits, post, singlets = cls._e_step_any(
                 pack, table, doublet_prior, prior_logits=prior_dev if iteration == 0 else None, want_singlets=True)
             post_np, logits_np, addition_np = _to_host(post, logits, addition)
             post_df = pd.DataFrame(data=post_np, index=barcode_handler.ordered_barcodes, columns=names, copy=False)
@@ -662,7 +750,8 @@ class Demultiplexer:
         E-step (whose result the reference discards, demux.py:55,113) is not run.
         """
         assert 0 <= doublet_prior < 1
-        assert not cls.aggregate_on_snps, 'aggregate_on_snps=True is not implemented on the CUDA path'
+        assert not (cls.aggregate_on_snps and cls.process_group is not None), \
+            'aggregate_on_snps=True is a single-GPU path'
         assert n_iterations >= 1, 'the reference unpacks the last generator item: n_iterations must be >= 1'
         n_cols = n_options(genotypes.n_genotypes, doublet_prior)
         if barcode_prior_logits is not None:
@@ -691,7 +780,7 @@ class Demultiplexer:
         for iteration in range(n_iterations):
             last = iteration == n_iterations - 1
             table = cls._probs_table(pack, addition, p_genotype_clip, out=table)
-            _, post, singlets = cls._e_step(
+            _, post, singlets = cls._e_step_any(
                 pack, table, doublet_prior, prior_logits=prior_logits if iteration == 0 else None,
                 want_logits=False, want_post=last, want_singlets=not last, buffers=buffers)
             if not last:

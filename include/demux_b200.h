@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DMX_ABI_VERSION 2
+#define DMX_ABI_VERSION 3
 
 /* E-step arithmetic flavours (see DESIGN.md "E-step") */
 #define DMX_ESTEP_EXACT 0 /* per-term float32 argument roundings + logf of demux.py:261, float64 accumulation */
@@ -182,6 +182,39 @@ int dmx_mstep_planned(const int64_t* variant_offsets, const int32_t* csc_cb, con
                       float* addition, int64_t ld_addition, double* addition64, int64_t ld_addition64,
                       int64_t variant_lo, int64_t variant_hi, const void* plan, int64_t n_rows, int64_t n_medium,
                       int64_t n_heavy_variants, int64_t n_heavy_items, double* heavy_scratch, void* stream);
+
+/* ---- per-(barcode, SNP) regularised likelihood: demux.py:204-244 (`Demultiplexer.aggregate_on_snps = True`) ----
+ * The reference's experimental alternative to (a9): matched molecule-level calls are grouped by
+ * (compressed_cb, snp_id) (FeatureLookup, utils.py:207-265); per group and column the float32 logs
+ * log(p_c[variant] + p_base_wrong) are summed in float64, divided by count ** compensation, log-softmaxed in
+ * float32, mixed with a uniform 0.01 / C "bad SNP" mass, log-softmaxed in float64 and summed per barcode.
+ * Logits and posteriors of this branch are float64, as in the reference (np.logaddexp against a float64 scalar).
+ *
+ * dmx_build_snp_groups: inputs are the outputs of dmx_unpack_match_calls over all chromosomes (variant -1 =
+ * unmatched) and variant2snp (genotypes.py:56-66) on the device; calls of barcodes outside [cb_lo, cb_hi) are
+ * skipped.  Outputs: the kept calls in group order -- ascending (barcode, SNP), original call order inside a
+ * group (stable sort) -- as grouped_variant / grouped_e [n_calls], group_offsets [n_calls + 1] (first n_groups + 1
+ * entries valid) and barcode_group_offsets [n_barcodes + 1] (groups of barcodes < b).  Synchronises `stream`;
+ * h_n_matched / h_n_groups (host) receive the counts.  n_calls < 2^31. */
+int64_t dmx_snp_groups_workspace_bytes(int64_t n_calls);
+int dmx_build_snp_groups(const int32_t* call_variant, const int32_t* call_cb, const float* call_e, int64_t n_calls,
+                         const int32_t* variant2snp, int64_t n_snps, int64_t n_barcodes, int64_t cb_lo, int64_t cb_hi,
+                         void* workspace, int64_t workspace_bytes, int32_t* grouped_variant, float* grouped_e,
+                         int64_t* group_offsets, int64_t* barcode_group_offsets, int64_t* h_n_matched,
+                         int64_t* h_n_groups, void* stream);
+/* logits[b, c] float64 [n_barcodes, C], C as in dmx_estep; `table` is the output of dmx_probs_from_betas.
+ * One warp per barcode, groups in order, no atomics: deterministic. */
+int64_t dmx_snp_logits_workspace_bytes(int64_t n_barcodes, int32_t n_cols);
+int dmx_snp_logits(const int64_t* barcode_group_offsets, const int64_t* group_offsets, const int32_t* grouped_variant,
+                   const float* grouped_e, int64_t n_barcodes, const float* table, int64_t ld_table,
+                   int32_t n_genotypes, double doublet_prior, double compensation, double* logits, int64_t ld_logits,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+/* float64 row softmax (demux.py:101,152 on this branch's logits).  prior_logits (may be NULL) is first added to
+ * `logits` in place (demux.py:97-99); posteriors (float64, may be NULL) and singlet_posteriors (float32 [n_rows,
+ * ld_singlet], the M-step's input, may be NULL) as in dmx_softmax_rows. */
+int dmx_softmax_rows_f64(double* logits, int64_t ld_logits, const double* prior_logits, int64_t ld_prior, int64_t n_rows,
+                         int32_t n_cols, double* posteriors, int64_t ld_post, float* singlet_posteriors,
+                         int64_t ld_singlet, int32_t n_singlets, void* stream);
 
 /* float32(out) = float32(in64) elementwise over a [rows, cols] matrix (after an all-reduce of float64 partials) */
 int dmx_round_f64_to_f32(const double* in64, int64_t ld_in, float* out, int64_t ld_out, int64_t n_rows,

@@ -23,4 +23,7 @@ from .demux_oracle import (  # noqa: F401
     barcode_logits,
     softmax_rows,
     m_step,
+    snp_groups,
+    snp_aggregated_logits,
+    log_softmax_rows,
 )

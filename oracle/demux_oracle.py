@@ -273,6 +273,67 @@ def softmax_rows(logits: np.ndarray) -> np.ndarray:
 
 
 # ----------------------------------------------------------------------------------------------
+# per-(barcode, SNP) regularised likelihood: `aggregate_on_snps = True`   demux.py:204-244
+# ----------------------------------------------------------------------------------------------
+
+P_BAD_SNP = 0.01  # demux.py:234
+
+
+def log_softmax_rows(x: np.ndarray) -> np.ndarray:
+    """scipy.special.log_softmax(x, axis=1) (scipy 1.18.1, special/_logsumexp.py) in the dtype of x."""
+    x_max = np.max(x, axis=1, keepdims=True)
+    x_max[~np.isfinite(x_max)] = 0
+    tmp = x - x_max
+    with np.errstate(divide='ignore'):
+        out = np.log(np.sum(np.exp(tmp), axis=1, keepdims=True))
+    return tmp - out
+
+
+def snp_groups(mol_cb, mol_snp):
+    """
+    Dense ids of the (compressed_cb, snp_id) groups, ascending in (barcode, SNP): what FeatureLookup
+    (utils.py:207-265) yields at demux.py:216-218, over int64 keys.  Returns
+    (group_of_call [M'], molecules per group [n_groups] int64, barcode of group [n_groups]).
+    """
+    cb, snp = np.asarray(mol_cb), np.asarray(mol_snp)
+    n_snp_categories = int(np.max(snp)) + 1  # utils.py:213 (raises on zero matched calls, as the reference does)
+    keys = cb.astype(np.int64) * n_snp_categories + snp
+    lookup, group_of_call = np.unique(keys, return_inverse=True)
+    counts = np.bincount(group_of_call, minlength=len(lookup))
+    return group_of_call, counts, lookup // n_snp_categories
+
+
+def snp_aggregated_logits(mol_variant, mol_snp, mol_cb, mol_e, table: np.ndarray, doublet_prior: float,
+                          n_barcodes: int, compensation: float = 0.5) -> np.ndarray:
+    """
+    Restates the `aggregate_on_snps=True` branch of compute_barcode_logits (demux.py:204-244): float64 [B, C].
+    Molecule-level calls are grouped per (barcode, SNP); a group's float32 log-likelihoods are divided by
+    count**compensation, passed through log_softmax, mixed with a uniform `P_BAD_SNP` (float64 from here on,
+    because np.log returns a float64 scalar), log_softmax-ed again and summed per barcode.  As in the
+    reference, the doublet penalties only fix the number of columns (demux.py:212) and are never added.
+    """
+    g = table.shape[1]
+    pairs = option_pairs(g, doublet_prior)
+    n_cols = len(pairs)
+    group_of_call, counts, group_barcode = snp_groups(mol_cb, mol_snp)
+    n_groups = len(counts)
+    table = np.asarray(table, dtype=np.float32)
+    e = np.asarray(mol_e, dtype=np.float32)
+    variant = np.asarray(mol_variant)
+    group_logits = np.zeros((n_groups, n_cols), dtype=np.float32)
+    for c, (i, j) in enumerate(pairs):
+        col = table[:, i] if i == j else (table[:, i] + table[:, j]) * np.float32(0.5)  # demux.py:180,190
+        log_pen = np.log(col[variant] + e)  # demux.py:227-228, float32
+        group_logits[:, c] = group_logits[:, c] + np.bincount(group_of_call, weights=log_pen, minlength=n_groups)
+    group_logits /= counts[:, None] ** compensation  # demux.py:231: float64 quotient stored as float32
+    group_logits = log_softmax_rows(group_logits)  # demux.py:233, float32
+    group_logits = np.logaddexp(group_logits, np.log(P_BAD_SNP / n_cols))  # demux.py:235 -> float64
+    group_logits = log_softmax_rows(group_logits)  # demux.py:236, float64
+    return np.stack([np.bincount(group_barcode, weights=col, minlength=n_barcodes) for col in group_logits.T],
+                    axis=1)  # demux.py:238-241
+
+
+# ----------------------------------------------------------------------------------------------
 # M-step                                                             demux.py:113-118
 # ----------------------------------------------------------------------------------------------
 
@@ -295,6 +356,8 @@ def m_step(rows_variant, rows_cb, rows_e, posteriors: np.ndarray, n_genotypes: i
 class OracleDemultiplexer:
     """Mirrors demuxalot.Demultiplexer (demux.py:24-392) on top of the functions above."""
     contribution_power = 2.
+    aggregate_on_snps = False  # demux.py:31; True selects snp_aggregated_logits (demux.py:204-244)
+    compensation_during_computing_barcode_logits = 0.5  # demux.py:32
     n_jobs = 1  # column-sharding of the E-step over processes (CPU baseline only)
 
     @staticmethod
@@ -310,7 +373,12 @@ class OracleDemultiplexer:
         return variant2snp, betas, molecule_calls, rows
 
     @classmethod
-    def _logits(cls, rows, table, doublet_prior, n_barcodes):
+    def _logits(cls, rows, table, doublet_prior, n_barcodes, molecule_calls=None):
+        if cls.aggregate_on_snps:  # demux.py:198
+            return snp_aggregated_logits(
+                molecule_calls['variant_id'], molecule_calls['snp_id'], molecule_calls['compressed_cb'],
+                molecule_calls['p_base_wrong'], table, doublet_prior, n_barcodes,
+                cls.compensation_during_computing_barcode_logits)
         return barcode_logits(rows['variant_id'], rows['compressed_cb'], rows['p_base_wrong'], table,
                               doublet_prior, n_barcodes, n_jobs=cls.n_jobs)
 
@@ -320,7 +388,7 @@ class OracleDemultiplexer:
         variant2snp, betas, _mol, rows = cls.pack_calls(chromosome2compressed_snp_calls, genotypes, False)
         table = probs_from_betas(variant2snp, betas, p_genotype_clip)
         assert np.isfinite(table).all()
-        logits = cls._logits(rows, table, doublet_prior, barcode_handler.n_barcodes)
+        logits = cls._logits(rows, table, doublet_prior, barcode_handler.n_barcodes, _mol)
         names = option_names(genotypes.genotype_names, doublet_prior)
         index = list(barcode_handler.ordered_barcodes)
         logits_df = pd.DataFrame(data=logits, index=index, columns=names)
@@ -342,7 +410,7 @@ class OracleDemultiplexer:
         addition = np.zeros_like(betas)
         for iteration in range(n_iterations):
             table = probs_from_betas(variant2snp, betas + addition, p_genotype_clip)
-            logits = cls._logits(rows, table, doublet_prior, barcode_handler.n_barcodes)
+            logits = cls._logits(rows, table, doublet_prior, barcode_handler.n_barcodes, _mol)
             if iteration == 0 and barcode_prior_logits is not None:
                 logits += barcode_prior_logits
             post = softmax_rows(logits)
