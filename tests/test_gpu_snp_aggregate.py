@@ -147,10 +147,13 @@ def test_runs_are_deterministic(D):
     assert np.array_equal(bits(a.values), bits(b.values))
 
 
-def test_flag_off_is_the_default_path(native_lib):
-    from demuxalot_b200 import Demultiplexer
-    assert Demultiplexer.aggregate_on_snps is False
-    case = load_case('g4_dp25')
-    logits_df, _ = Demultiplexer.predict_posteriors(case.calls, case.genotypes, case.barcode_handler,
-                                                    doublet_prior=case.doublet_prior)
-    assert logits_df.values.dtype == np.float32
+def test_flag_off_selects_the_float32_path(D):
+    D.aggregate_on_snps = False  # the module fixture holds it at True
+    try:
+        case = load_case('g4_dp25')
+        logits_df, _ = D.predict_posteriors(case.calls, case.genotypes, case.barcode_handler,
+                                            doublet_prior=case.doublet_prior)
+        assert logits_df.values.dtype == np.float32
+        np.testing.assert_allclose(logits_df.values, case.fx['predict_logits'], rtol=1e-5)
+    finally:
+        D.aggregate_on_snps = True
