@@ -9,8 +9,9 @@
 //
 //   dmx_build_snp_groups   stable radix sort of (cb * n_snps + snp) keys (CUB, library code as in builder.cu) and the
 //                          kernels below: calls in group order, group offsets, groups per barcode;
-//   dmx_snp_logits         one warp per barcode walks its groups in order, lanes stride the columns; the reductions
-//                          over columns are warp shuffles, the per-barcode sum is sequential: no atomics, deterministic;
+//   dmx_snp_logits         one CTA per barcode: its warps take the barcode's groups round-robin, lanes stride the
+//                          columns, the reductions over columns are warp shuffles; every warp sums its groups in order
+//                          and the CTA adds the warps' partial rows in warp order: no atomics, deterministic;
 //   dmx_softmax_rows_f64   float64 row softmax (+ the optional prior logits of the first EM iteration).
 //
 // Arithmetic follows the reference's dtypes step by step; the float32 sum of exponentials is taken lane-strided
@@ -124,18 +125,19 @@ __global__ void __launch_bounds__(32 * SNP_WARPS_PER_CTA) snp_logits_kernel(
     const int32_t* __restrict__ grouped_variant, const float* __restrict__ grouped_e, int64_t n_barcodes,
     const float* __restrict__ table, int64_t ld_table, int n_cols, const int32_t* __restrict__ pairs, double log_bad,
     double compensation, double* __restrict__ logits, int64_t ld_logits, float* scratch32, double* scratch64,
-    int64_t scratch_ld) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = blockIdx.x * (int64_t)SNP_WARPS_PER_CTA + (threadIdx.x >> 5);
-    const int64_t n_warps = gridDim.x * (int64_t)SNP_WARPS_PER_CTA;
-    // a lane only ever reads back the scratch entries it wrote itself (columns lane, lane + 32, ...)
-    float* xs = scratch32 + warp * scratch_ld;
-    double* ts = scratch64 + warp * scratch_ld;
-    for (int64_t b = warp; b < n_barcodes; b += n_warps) {
-        double* acc = logits + b * ld_logits;
-        for (int c = lane; c < n_cols; c += 32) acc[c] = 0.0;
+    double* scratch_part, int64_t scratch_ld) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t slot = blockIdx.x * (int64_t)SNP_WARPS_PER_CTA + w;
+    // a lane only ever reads back the xs / ts entries it wrote itself (columns lane, lane + 32, ...); the partial rows
+    // are read by the whole CTA after a barrier
+    float* xs = scratch32 + slot * scratch_ld;
+    double* ts = scratch64 + slot * scratch_ld;
+    double* part = scratch_part + slot * scratch_ld;
+    const double* cta_parts = scratch_part + blockIdx.x * (int64_t)SNP_WARPS_PER_CTA * scratch_ld;
+    for (int64_t b = blockIdx.x; b < n_barcodes; b += gridDim.x) {
+        for (int c = lane; c < n_cols; c += 32) part[c] = 0.0;
         const int64_t q_lo = barcode_group_offsets[b], q_hi = barcode_group_offsets[b + 1];
-        for (int64_t q = q_lo; q < q_hi; ++q) {
+        for (int64_t q = q_lo + w; q < q_hi; q += SNP_WARPS_PER_CTA) {
             const int64_t lo = group_offsets[q], hi = group_offsets[q + 1];
             // counts ** compensation (demux.py:231); 0.5 is the reference's constant and sqrt is correctly rounded
             const double denom = compensation == 0.5 ? sqrt((double)(hi - lo)) : pow((double)(hi - lo), compensation);
@@ -168,8 +170,16 @@ __global__ void __launch_bounds__(32 * SNP_WARPS_PER_CTA) snp_logits_kernel(
                 s2 += exp(t);
             }
             const double l2 = log(warp_sum(s2));
-            for (int c = lane; c < n_cols; c += 32) acc[c] += ts[c] - l2;
+            for (int c = lane; c < n_cols; c += 32) part[c] += ts[c] - l2;
         }
+        __syncthreads();  // the partial rows of all warps are complete and visible to the CTA
+        for (int c = threadIdx.x; c < n_cols; c += 32 * SNP_WARPS_PER_CTA) {
+            double total = 0.0;
+#pragma unroll
+            for (int k = 0; k < SNP_WARPS_PER_CTA; ++k) total += cta_parts[k * scratch_ld + c];
+            logits[b * ld_logits + c] = total;
+        }
+        __syncthreads();  // before the next barcode zeroes the partial rows
     }
 }
 
@@ -224,9 +234,19 @@ static inline int snp_grid(int64_t n, int threads) {
     return (int)(blocks < cap ? blocks : cap);
 }
 
-static inline int64_t snp_logits_warps(int64_t n_barcodes) {
-    const int64_t cap = (int64_t)sm_count() * 4 * SNP_WARPS_PER_CTA;
-    const int64_t want = round_up(n_barcodes > 0 ? n_barcodes : 1, SNP_WARPS_PER_CTA);
+// persistent CTAs: one per barcode, at most as many as are resident at once (a CTA of a second wave would only start
+// once a first-wave CTA has finished all of its barcodes)
+static inline int64_t snp_logits_ctas(int64_t n_barcodes) {
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, snp_logits_kernel, 32 * SNP_WARPS_PER_CTA, 0) != cudaSuccess ||
+            n <= 0)
+            n = 2;
+        per_sm = n;
+    }
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    const int64_t want = n_barcodes > 0 ? n_barcodes : 1;
     return want < cap ? want : cap;
 }
 
@@ -311,7 +331,9 @@ int64_t dmx_snp_logits_workspace_bytes(int64_t n_barcodes, int32_t n_cols) {
     using namespace dmx;
     if (n_cols <= 0) return 0;
     const int64_t ld = round_up(n_cols, 32);
-    return round_up(4 * (int64_t)n_cols, 256) + snp_logits_warps(n_barcodes) * ld * (int64_t)(sizeof(float) + sizeof(double));
+    // pair table + per warp: float32 staging row, float64 staging row, float64 partial sums
+    return round_up(4 * (int64_t)n_cols, 256) +
+           snp_logits_ctas(n_barcodes) * SNP_WARPS_PER_CTA * ld * (int64_t)(sizeof(float) + 2 * sizeof(double));
 }
 
 int dmx_snp_logits(const int64_t* barcode_group_offsets, const int64_t* group_offsets, const int32_t* grouped_variant,
@@ -331,17 +353,19 @@ int dmx_snp_logits(const int64_t* barcode_group_offsets, const int64_t* group_of
                 (long long)need);
     cudaStream_t stream = (cudaStream_t)stream_;
     const int64_t ld = round_up(n_cols, 32);
-    const int64_t n_warps = snp_logits_warps(n_barcodes);
+    const int64_t n_ctas = snp_logits_ctas(n_barcodes);
+    const int64_t n_warps = n_ctas * SNP_WARPS_PER_CTA;
     uint8_t* ws = (uint8_t*)workspace;
     int32_t* pairs = (int32_t*)ws; ws += round_up(4 * (int64_t)n_cols, 256);
     double* scratch64 = (double*)ws; ws += n_warps * ld * (int64_t)sizeof(double);
+    double* scratch_part = (double*)ws; ws += n_warps * ld * (int64_t)sizeof(double);
     float* scratch32 = (float*)ws;
     snp_pairs_kernel<<<(int)ceil_div(n_cols, 256), 256, 0, stream>>>(n_genotypes, n_cols, pairs);
     DMX_LAUNCH_CHECK();
     const double log_bad = log(0.01 / (double)n_cols);  // demux.py:234-235: np.log(p_bad_snp / len(column_names))
-    snp_logits_kernel<<<(int)(n_warps / SNP_WARPS_PER_CTA), 32 * SNP_WARPS_PER_CTA, 0, stream>>>(
+    snp_logits_kernel<<<(int)n_ctas, 32 * SNP_WARPS_PER_CTA, 0, stream>>>(
         barcode_group_offsets, group_offsets, grouped_variant, grouped_e, n_barcodes, table, ld_table, n_cols, pairs,
-        log_bad, compensation, logits, ld_logits, scratch32, scratch64, ld);
+        log_bad, compensation, logits, ld_logits, scratch32, scratch64, scratch_part, ld);
     DMX_LAUNCH_CHECK();
     return 0;
 }

@@ -1,5 +1,6 @@
 """CPU emulation (numpy, scalar loops) of the index logic and pass structure of csrc/snp_aggregate.cu, checked against
-the oracle on a golden case with unmatched calls mixed in.  A development aid for a container without a GPU:
+the oracle on a golden case with unmatched calls mixed in (the kernel now adds the groups of a barcode per warp and
+combines 8 partial rows; this emulation keeps the sequential order: same values up to float64 regrouping).  A development aid for a container without a GPU:
 python scripts/emulate_snp_aggregate.py"""
 import math
 import sys
