@@ -118,14 +118,14 @@ if (SRC / 'launches.csv').exists():
 for rep, name in (('prof_estep_full.ncu-rep', 'estep_pairs'), ('prof_aux.ncu-rep', 'mstep_singlets_table_softmax'),
                   ('prof_patch.ncu-rep', 'estep_pairs_patch_g200'), ('prof_singlets.ncu-rep', 'estep_singlets'),
                   ('r01b_mstep_light.ncu-rep', 'mstep_light_tier'), ('prof_mstep_tiers.ncu-rep', 'mstep_tiers'),
-                  ('prof_small.ncu-rep', 'estep_lane_per_row_g4')):
+                  ('prof_small.ncu-rep', 'estep_lane_per_row_g4'), ('prof_snp_logits.ncu-rep', 'snp_logits')):
     if (SRC / rep).exists():
         traffic = summarise_report(SRC / rep, name)
         if name == 'estep_pairs' and traffic:
             (OUT / 'estep_traffic.json').write_text(json.dumps({
                 'kernel': 'estep_pairs_warp_kernel', 'dram_bytes_per_launch': traffic, 'source': f'{tag}_ncu_{name}.txt',
                 'workload': 'pbmc_32 scale 1.0 (R = 20.07 M rows, G = 32)'}) + '\n')
-for f in ('microbench.log', 'microbench_packed_tile.log', 'bench_mstep.log', 'config4_shard.log', 'parity_report.json', 'profile_e2e.log', 'bench.log', 'bench_n2.log', 'bench_n8.log',
+for f in ('microbench.log', 'microbench_packed_tile.log', 'bench_mstep.log', 'sweep_table.log', 'bench_snp_aggregate.log', 'parity_report_snp_aggregate.json', 'config4_shard.log', 'parity_report.json', 'profile_e2e.log', 'bench.log', 'bench_n2.log', 'bench_n8.log',
           'bench_reference.log', 'sweep_g32_c.log', 'sweep_g200_c.log', 'sanitizer.log', 'pytest_gpu.log',
           'pytest_dist.log'):
     if (SRC / f).exists():

@@ -19,5 +19,10 @@ ncu --set full --clock-control none --import-source on -k regex:estep_pairs_patc
 python scripts/run_config4_shard.py > gpurun_out/config4_shard.log 2>&1
 python scripts/profile_e2e.py > gpurun_out/profile_e2e.log 2>&1
 python scripts/bench_mstep.py > gpurun_out/bench_mstep.log 2>&1
+(python scripts/sweep_table.py 32 656584; python scripts/sweep_table.py 200 1000000) > gpurun_out/sweep_table.log 2>&1
+python scripts/bench_snp_aggregate.py 0.25 > gpurun_out/bench_snp_aggregate.log 2>&1
+# aggregate_on_snps E-step: tens of ms per launch and ~40 replays -- a tenth of the workload and a generous limit
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:snp_logits -c 1 -f -o gpurun_out/prof_snp_logits \
+    python scripts/bench_snp_aggregate.py 0.1 > gpurun_out/ncu_snp_logits.log 2>&1
 timeout 600 compute-sanitizer --tool memcheck python __graft_entry__.py smoke 2>&1 | tail -15 > gpurun_out/sanitizer.log
 tail -3 gpurun_out/pytest_gpu.log; tail -c 1500 gpurun_out/bench.log; echo; tail -c 600 gpurun_out/bench_reference.log; echo; tail -4 gpurun_out/sanitizer.log
