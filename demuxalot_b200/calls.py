@@ -79,17 +79,23 @@ class CompressedSNPCalls:
     @staticmethod
     def concatenate(snp_calls_list: Iterable['CompressedSNPCalls']) -> 'CompressedSNPCalls':
         """Merge containers of the same chromosome; molecule indices are rebased (snp_counter.py:120-139)."""
-        mols: List[np.ndarray] = []
-        calls: List[np.ndarray] = []
-        base = 0
-        for part in snp_calls_list:
-            c = part.snp_calls[:part.n_snp_calls].copy()
-            c['molecule_index'] += base
-            calls.append(c)
-            mols.append(part.molecules[:part.n_molecules])
-            base += part.n_molecules
+        parts = list(snp_calls_list)
         out = CompressedSNPCalls.__new__(CompressedSNPCalls)
-        out.molecules = np.concatenate(mols) if mols else _blank(MOLECULE_DTYPE, 0, (-1, -1, -1.))
-        out.snp_calls = np.concatenate(calls) if calls else _blank(SNP_CALL_DTYPE, 0, (-1, -1, 255, -1.))
+        if not parts:
+            out.molecules = _blank(MOLECULE_DTYPE, 0, (-1, -1, -1.))
+            out.snp_calls = _blank(SNP_CALL_DTYPE, 0, (-1, -1, 255, -1.))
+        else:
+            # every record is copied once, straight into its place in the result
+            out.molecules = np.empty(sum(p.n_molecules for p in parts), dtype=parts[0].molecules.dtype)
+            out.snp_calls = np.empty(sum(p.n_snp_calls for p in parts), dtype=parts[0].snp_calls.dtype)
+            base = first_call = 0
+            for part in parts:
+                out.molecules[base:base + part.n_molecules] = part.molecules[:part.n_molecules]
+                block = out.snp_calls[first_call:first_call + part.n_snp_calls]
+                block[...] = part.snp_calls[:part.n_snp_calls]
+                if base:
+                    block['molecule_index'] += base
+                base += part.n_molecules
+                first_call += part.n_snp_calls
         out.n_molecules, out.n_snp_calls = len(out.molecules), len(out.snp_calls)
         return out

@@ -10,6 +10,8 @@ The BAM itself is read by `demuxalot_b200.bam` (zlib + struct), so the stage run
 """
 from __future__ import annotations
 
+import os
+
 from collections import defaultdict
 from pathlib import Path
 from typing import Callable, Dict, List, Optional, Tuple
@@ -196,7 +198,22 @@ def _bam_info(path) -> dict:
 
 
 def _whitelist_blob(barcode_handler: BarcodeHandler):
-    """Whitelist keys as one byte blob + offsets + compressed ids (tuple keys (CB, RG) are joined with 0x1f)."""
+    """Whitelist keys as one byte blob + offsets + compressed ids (tuple keys (CB, RG) are joined with 0x1f).
+    Built once per handler: every region task of a BAM passes the same whitelist."""
+    mapping = barcode_handler.barcode2index
+    stamp = (id(mapping), len(mapping))
+    cached = getattr(barcode_handler, '_native_whitelist', None)
+    if cached is not None and cached[0] == stamp:
+        return cached[1]
+    blob = _build_whitelist_blob(barcode_handler)
+    try:
+        barcode_handler._native_whitelist = (stamp, blob)
+    except AttributeError:  # a handler type that does not take attributes: rebuild per task
+        pass
+    return blob
+
+
+def _build_whitelist_blob(barcode_handler: BarcodeHandler):
     keys, ids = [], []
     for key, idx in barcode_handler.barcode2index.items():
         if isinstance(key, tuple):
@@ -351,6 +368,15 @@ def plan_tasks(bamfile_location, chromosome2positions: Dict[str, np.ndarray], ba
     return [task for _complexity, task in sorted(ranked, reverse=True)]
 
 
+def _resolve_n_jobs(n_jobs) -> int:
+    """joblib's convention: -1 = all cores, -2 = all but one, ..."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    if n_jobs is None:
+        return 1
+    n_jobs = int(n_jobs)
+    return max(1, cores + 1 + n_jobs) if n_jobs < 0 else max(1, n_jobs)
+
+
 def count_snps(bamfile_location, chromosome2positions: Dict[str, np.ndarray], barcode_handler: BarcodeHandler,
                joblib_n_jobs=-1, joblib_verbosity=11, parse_read=parse_read,
                use_native: bool = True) -> Dict[str, CompressedSNPCalls]:
@@ -368,8 +394,15 @@ def count_snps(bamfile_location, chromosome2positions: Dict[str, np.ndarray], ba
         return count_region(bamfile, chromosome, positions, handler, parse_read, start=start, stop=stop,
                             use_native=use_native)
 
+    native = use_native and native_io() is not None and parse_read in _NATIVE_FILTERS
     if joblib_n_jobs == 1 or len(tasks) <= 1:
         results = [run(task) for task in tasks]
+    elif native:
+        # the native loop runs outside the GIL (ctypes): threads of this process, nothing to pickle back (the
+        # reference's worker processes return tens of MB per task); same tasks, same order of results
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(_resolve_n_jobs(joblib_n_jobs), len(tasks))) as pool:
+            results = list(pool.map(run, tasks))
     else:
         import joblib
         with joblib.Parallel(n_jobs=joblib_n_jobs, verbose=joblib_verbosity, pre_dispatch='all') as parallel:
@@ -379,4 +412,6 @@ def count_snps(bamfile_location, chromosome2positions: Dict[str, np.ndarray], ba
     per_chromosome = defaultdict(list)
     for chromosome, calls in results:
         per_chromosome[chromosome].append(calls)
-    return {chromosome: CompressedSNPCalls.concatenate(parts) for chromosome, parts in per_chromosome.items()}
+    # a chromosome counted by one task keeps that task's (tight, unshared) arrays: nothing to merge or copy
+    return {chromosome: parts[0] if len(parts) == 1 else CompressedSNPCalls.concatenate(parts)
+            for chromosome, parts in per_chromosome.items()}

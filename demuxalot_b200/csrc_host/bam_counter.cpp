@@ -40,6 +40,7 @@ public:
     }
     ~Bgzf() {
         if (file_) fclose(file_);
+        if (inflater_ready_) inflateEnd(&inflater_);
     }
     void seek(uint64_t voffset) {
         if (fseeko(file_, (off_t)(voffset >> 16), SEEK_SET) != 0) throw Fail{"seek failed"};
@@ -87,7 +88,8 @@ private:
             if (got == 0) return false;
             if (got != 12 || header[0] != 0x1F || header[1] != 0x8B) throw Fail{"not a BGZF stream"};
             const unsigned xlen = header[10] | (header[11] << 8);
-            std::vector<uint8_t> extra(xlen);
+            std::vector<uint8_t>& extra = extra_;
+            extra.resize(xlen);
             if (fread(extra.data(), 1, xlen, file_) != xlen) throw Fail{"truncated BGZF header"};
             int block_size = -1;
             for (size_t p = 0; p + 4 <= xlen;) {
@@ -104,22 +106,27 @@ private:
             block_.resize(isize);
             cursor_ = 0;
             if (isize == 0) continue;  // empty block (EOF marker): try the next one
-            z_stream zs;
-            memset(&zs, 0, sizeof(zs));
-            if (inflateInit2(&zs, -15) != Z_OK) throw Fail{"zlib init failed"};
-            zs.next_in = compressed_.data();
-            zs.avail_in = (uInt)payload;
-            zs.next_out = block_.data();
-            zs.avail_out = (uInt)isize;
-            const int rc = inflate(&zs, Z_FINISH);
-            inflateEnd(&zs);
-            if (rc != Z_STREAM_END) throw Fail{"zlib inflate failed"};
+            // one inflate state for the whole stream, reset per block (raw deflate members)
+            if (!inflater_ready_) {
+                memset(&inflater_, 0, sizeof(inflater_));
+                if (inflateInit2(&inflater_, -15) != Z_OK) throw Fail{"zlib init failed"};
+                inflater_ready_ = true;
+            } else if (inflateReset(&inflater_) != Z_OK) {
+                throw Fail{"zlib reset failed"};
+            }
+            inflater_.next_in = compressed_.data();
+            inflater_.avail_in = (uInt)payload;
+            inflater_.next_out = block_.data();
+            inflater_.avail_out = (uInt)isize;
+            if (inflate(&inflater_, Z_FINISH) != Z_STREAM_END) throw Fail{"zlib inflate failed"};
             return true;
         }
     }
     FILE* file_;
-    std::vector<uint8_t> compressed_, block_;
+    std::vector<uint8_t> compressed_, block_, extra_;
     size_t cursor_ = 0;
+    z_stream inflater_;
+    bool inflater_ready_ = false;
 };
 
 // ---------------------------------------------------------------------------------------------- BAM records
@@ -129,16 +136,18 @@ struct Read {
     uint8_t mapq;
     uint16_t flag;
     std::vector<uint32_t> cigar;
-    std::vector<uint8_t> seq;   // 4-bit packed
-    std::vector<uint8_t> qual;
-    std::vector<uint8_t> tags;
+    // views into the record buffer of next_read(): valid until the next record is read
+    const uint8_t* seq = nullptr;   // 4-bit packed
+    const uint8_t* qual = nullptr;
+    const uint8_t* tags = nullptr;
+    size_t n_tags = 0;
 
     char base(int k) const { return "=ACMGRSVTWYHKDBN"[(seq[k >> 1] >> ((k & 1) ? 0 : 4)) & 0xF]; }
 
     // integer / string tag lookup; returns false when absent
     bool find_tag(const char* name, int64_t* as_int, std::string* as_str) const {
         size_t off = 0;
-        const size_t n = tags.size();
+        const size_t n = n_tags;
         while (off + 3 <= n) {
             const bool hit = tags[off] == (uint8_t)name[0] && tags[off + 1] == (uint8_t)name[1];
             const char kind = (char)tags[off + 2];
@@ -206,11 +215,13 @@ bool next_read(Bgzf& in, Read& r, std::vector<uint8_t>& scratch) {
     r.cigar.resize(n_cigar);
     if (n_cigar) memcpy(r.cigar.data(), p + off, 4 * (size_t)n_cigar);
     off += 4 * (size_t)n_cigar;
-    r.seq.assign(p + off, p + off + (l_seq + 1) / 2);
+    r.seq = p + off;
     off += (size_t)(l_seq + 1) / 2;
-    r.qual.assign(p + off, p + off + l_seq);
+    r.qual = p + off;
     off += (size_t)l_seq;
-    r.tags.assign(p + off, p + block_size);
+    if (off > (size_t)block_size) throw Fail{"corrupt BAM record"};
+    r.tags = p + off;
+    r.n_tags = (size_t)block_size - off;
     int32_t span = 0;
     for (uint32_t c : r.cigar) {
         const unsigned op = c & 0xF;
@@ -292,50 +303,24 @@ struct Counter {
         }
     }
 
-    void close_group(const Group& g) {
-        if (!any_in(g.min_start, (int64_t)g.max_end + 1)) return;
-        double p_group = 1.0;
-        std::vector<int32_t> order;                                   // SNP positions in first-seen order
-        std::unordered_map<int32_t, std::vector<Observation>> seen;   // position -> observations in read order
-        std::vector<const GroupRead*> unique;
-        for (const GroupRead& r : g.reads) {
-            bool duplicate = false;
-            for (const GroupRead* u : unique)
-                if (u->start == r.start && u->end == r.end && u->score == r.score) { duplicate = true; break; }
-            if (duplicate) continue;
-            unique.push_back(&r);
-            p_group *= r.p_misaligned;
-            for (const auto& call : r.calls) {
-                auto it = seen.find(call.first);
-                if (it == seen.end()) {
-                    order.push_back(call.first);
-                    it = seen.emplace(call.first, std::vector<Observation>()).first;
-                }
-                it->second.push_back(call.second);
-            }
+    // 0.1 ** (0.1 * q) for q = 0..40, each value produced by the same run-time libm pow call CPython makes
+    // (snp_counter.py:204); volatile keeps the compiler from folding the calls at build time with other roundings
+    double quality_factor[41];
+    Counter() {
+        for (int q = 0; q <= 40; ++q) {
+            volatile double exponent = 0.1 * (double)q;
+            quality_factor[q] = pow(0.1, exponent);
         }
-        struct Candidate { char base; double p_wrong; };
-        std::vector<std::pair<int32_t, Candidate>> emitted;
-        for (int32_t position : order) {
-            std::vector<Candidate> candidates;  // in first-seen order of the base
-            for (const Observation& o : seen[position]) {
-                const double factor = pow(0.1, 0.1 * (double)std::min<int>(o.quality, 40));
-                bool found = false;
-                for (Candidate& c : candidates)
-                    if (c.base == o.base) { c.p_wrong *= factor; found = true; break; }
-                if (!found) candidates.push_back({o.base, 1 * factor});
-            }
-            if (candidates.size() > 1) {
-                double best = candidates[0].p_wrong;
-                for (const Candidate& c : candidates) best = std::min(best, c.p_wrong);
-                std::vector<Candidate> kept;
-                for (const Candidate& c : candidates)
-                    if (c.p_wrong <= best * 1000) kept.push_back(c);
-                candidates.swap(kept);
-            }
-            if (candidates.size() == 1) emitted.push_back({position, candidates[0]});
-        }
-        if (emitted.empty()) return;
+    }
+
+    struct Candidate { char base; double p_wrong; };
+    struct Item { int32_t position; uint32_t seq; Observation obs; };          // one observation of a group
+    struct Emitted { uint32_t first_seq; int32_t position; Candidate call; };   // one call of a molecule
+    std::vector<Item> items_;        // scratch of close_group, reused from group to group
+    std::vector<Emitted> emitted_;
+    std::vector<const GroupRead*> unique_;
+
+    void append_molecule(const Group& g, double p_group) {
         const int32_t molecule = (int32_t)n_molecules++;
         const int32_t ub32 = (int32_t)g.ub;
         const float p_group32 = (float)p_group;
@@ -344,17 +329,77 @@ struct Counter {
         memcpy(&molecules[m], &g.cb, 4);
         memcpy(&molecules[m + 4], &ub32, 4);
         memcpy(&molecules[m + 8], &p_group32, 4);
-        for (const auto& e : emitted) {
-            const size_t c = calls.size();
-            calls.resize(c + 13);
-            const uint8_t code = (uint8_t)base_code(e.second.base);
-            const float p32 = (float)e.second.p_wrong;
+        size_t c = calls.size();
+        calls.resize(c + 13 * emitted_.size());
+        for (const Emitted& e : emitted_) {
+            const uint8_t code = (uint8_t)base_code(e.call.base);
+            const float p32 = (float)e.call.p_wrong;
             memcpy(&calls[c], &molecule, 4);
-            memcpy(&calls[c + 4], &e.first, 4);
+            memcpy(&calls[c + 4], &e.position, 4);
             calls[c + 8] = code;
             memcpy(&calls[c + 9], &p32, 4);
-            ++n_calls;
+            c += 13;
         }
+        n_calls += (int64_t)emitted_.size();
+    }
+
+    void close_group(const Group& g) {
+        if (!any_in(g.min_start, (int64_t)g.max_end + 1)) return;
+        double p_group = 1.0;
+        unique_.clear();
+        for (const GroupRead& r : g.reads) {
+            bool duplicate = false;
+            for (const GroupRead* u : unique_)
+                if (u->start == r.start && u->end == r.end && u->score == r.score) { duplicate = true; break; }
+            if (duplicate) continue;
+            unique_.push_back(&r);
+            p_group *= r.p_misaligned;
+        }
+        emitted_.clear();
+        if (unique_.size() == 1) {
+            // one read: its positions are strictly ascending, so every position has exactly one observation, one
+            // candidate, and yields a call with p_wrong = 1 * 0.1^(0.1 min(q, 40)), in the read's own order
+            for (const auto& call : unique_[0]->calls)
+                emitted_.push_back({0u, call.first,
+                                    Candidate{call.second.base, 1 * quality_factor[std::min<int>(call.second.quality, 40)]}});
+        } else {
+            // several reads: observations sorted by (position, arrival); a position's rank in first-seen order is the
+            // arrival number of its first observation, and the calls are emitted in that order
+            items_.clear();
+            uint32_t seq = 0;
+            for (const GroupRead* r : unique_)
+                for (const auto& call : r->calls) items_.push_back({call.first, seq++, call.second});
+            std::sort(items_.begin(), items_.end(), [](const Item& a, const Item& b) {
+                return a.position != b.position ? a.position < b.position : a.seq < b.seq;
+            });
+            for (size_t lo = 0; lo < items_.size();) {
+                size_t hi = lo;
+                Candidate candidates[16];  // in first-seen order of the base; a BAM base has 16 possible codes
+                int n_candidates = 0;
+                for (; hi < items_.size() && items_[hi].position == items_[lo].position; ++hi) {
+                    const Observation& o = items_[hi].obs;
+                    const double factor = quality_factor[std::min<int>(o.quality, 40)];
+                    bool found = false;
+                    for (int k = 0; k < n_candidates; ++k)
+                        if (candidates[k].base == o.base) { candidates[k].p_wrong *= factor; found = true; break; }
+                    if (!found) candidates[n_candidates++] = {o.base, 1 * factor};
+                }
+                if (n_candidates > 1) {  // the 1000x rule (snp_counter.py:207-210)
+                    double best = candidates[0].p_wrong;
+                    for (int k = 0; k < n_candidates; ++k) best = std::min(best, candidates[k].p_wrong);
+                    int kept = 0;
+                    for (int k = 0; k < n_candidates; ++k)
+                        if (candidates[k].p_wrong <= best * 1000) candidates[kept++] = candidates[k];
+                    n_candidates = kept;
+                }
+                if (n_candidates == 1) emitted_.push_back({items_[lo].seq, items_[lo].position, candidates[0]});
+                lo = hi;
+            }
+            std::sort(emitted_.begin(), emitted_.end(),
+                      [](const Emitted& a, const Emitted& b) { return a.first_seq < b.first_seq; });
+        }
+        if (emitted_.empty()) return;
+        append_molecule(g, p_group);
     }
 };
 
@@ -366,10 +411,65 @@ int64_t hash_umi(const std::string& s) {
     return (int64_t)value;
 }
 
-struct KeyHash {
-    size_t operator()(const std::pair<int32_t, int64_t>& k) const {
-        return std::hash<uint64_t>()(((uint64_t)(uint32_t)k.first << 32) ^ (uint64_t)k.second * 0x9E3779B97F4A7C15ull);
+// (barcode index, hashed UMI) -> slot of the open group: linear probing over one flat array, deletion by backward
+// shift (no tombstones), keys packed into 64 bits (the UMI hash is < 2^31, utils.py:12-22)
+class OpenIndex {
+public:
+    OpenIndex() { resize(1024); }
+    static uint64_t pack(int32_t cb, int64_t ub) { return ((uint64_t)(uint32_t)cb << 32) | (uint64_t)(uint32_t)ub; }
+    // slot of `key`, or -1
+    int64_t find(uint64_t key) const {
+        for (size_t i = mix(key) & mask_;; i = (i + 1) & mask_) {
+            if (keys_[i] == key) return (int64_t)values_[i];
+            if (keys_[i] == EMPTY) return -1;
+        }
     }
+    void insert(uint64_t key, size_t value) {  // key must be absent
+        if ((size_ + 1) * 4 > (mask_ + 1) * 3) resize(2 * (mask_ + 1));
+        size_t i = mix(key) & mask_;
+        while (keys_[i] != EMPTY) i = (i + 1) & mask_;
+        keys_[i] = key;
+        values_[i] = value;
+        ++size_;
+    }
+    void erase(uint64_t key) {
+        size_t i = mix(key) & mask_;
+        while (keys_[i] != key) {
+            if (keys_[i] == EMPTY) return;
+            i = (i + 1) & mask_;
+        }
+        --size_;
+        for (size_t j = (i + 1) & mask_;; j = (j + 1) & mask_) {  // close the gap so that probe chains stay intact
+            if (keys_[j] == EMPTY) break;
+            const size_t home = mix(keys_[j]) & mask_;
+            if (((j - home) & mask_) >= ((j - i) & mask_)) {
+                keys_[i] = keys_[j];
+                values_[i] = values_[j];
+                i = j;
+            }
+        }
+        keys_[i] = EMPTY;
+    }
+
+private:
+    static constexpr uint64_t EMPTY = ~0ull;  // cb = -1 never occurs: barcode indices are >= 0
+    static size_t mix(uint64_t k) {
+        k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+        return (size_t)k;
+    }
+    void resize(size_t capacity) {
+        std::vector<uint64_t> old_keys(capacity, EMPTY);
+        std::vector<size_t> old_values(capacity);
+        old_keys.swap(keys_);
+        old_values.swap(values_);
+        mask_ = capacity - 1;
+        size_ = 0;
+        for (size_t i = 0; i < old_keys.size(); ++i)
+            if (old_keys[i] != EMPTY) insert(old_keys[i], old_values[i]);
+    }
+    std::vector<uint64_t> keys_;
+    std::vector<size_t> values_;
+    size_t mask_ = 0, size_ = 0;
 };
 
 }  // namespace
@@ -405,7 +505,7 @@ dmxio_result* dmxio_count_region(const char* bam_path, int32_t ref_id, uint64_t 
         counter.n_positions = n_positions;
 
         std::vector<Group> groups;                                   // insertion order
-        std::unordered_map<std::pair<int32_t, int64_t>, size_t, KeyHash> open_index;
+        OpenIndex open_index;
         size_t first_open = 0;
         auto flush = [&](double threshold) {
             for (size_t k = first_open; k < groups.size(); ++k) {
@@ -413,7 +513,7 @@ dmxio_result* dmxio_count_region(const char* bam_path, int32_t ref_id, uint64_t 
                 if (g.open && (double)g.reach < threshold) {
                     counter.close_group(g);
                     g.open = false;
-                    open_index.erase({g.cb, g.ub});
+                    open_index.erase(OpenIndex::pack(g.cb, g.ub));
                     std::vector<GroupRead>().swap(g.reads);
                 }
             }
@@ -461,16 +561,16 @@ dmxio_result* dmxio_count_region(const char* bam_path, int32_t ref_id, uint64_t 
             // ---- add to its (barcode, UMI) group ----
             counter.calls_of_read(read, calls);
             GroupRead gr{read.pos, read.end, score, p_misaligned_default, calls};
-            const std::pair<int32_t, int64_t> key{cb, ub};
-            auto slot = open_index.find(key);
-            if (slot == open_index.end()) {
-                open_index.emplace(key, groups.size());
+            const uint64_t key = OpenIndex::pack(cb, ub);
+            const int64_t slot = open_index.find(key);
+            if (slot < 0) {
+                open_index.insert(key, groups.size());
                 Group g;
                 g.cb = cb; g.ub = ub; g.reach = read.end; g.min_start = read.pos; g.max_end = read.end;
                 g.reads.push_back(std::move(gr));
                 groups.push_back(std::move(g));
             } else {
-                Group& g = groups[slot->second];
+                Group& g = groups[(size_t)slot];
                 g.reach = std::max(g.reach, read.end);
                 g.min_start = std::min(g.min_start, read.pos);
                 g.max_end = std::max(g.max_end, read.end);

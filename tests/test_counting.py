@@ -203,6 +203,12 @@ def test_native_and_python_loops_agree_on_a_random_bam(tmp_path):
     native = count_snps(str(path), positions, handler, joblib_n_jobs=1, use_native=True)
     python = count_snps(str(path), positions, handler, joblib_n_jobs=1, use_native=False)
     assert list(native) == list(python)
+    # region tasks on a thread pool (the native loop runs outside the GIL): same records, same order
+    threaded = count_snps(str(path), positions, handler, joblib_n_jobs=2, use_native=True)
+    assert list(threaded) == list(native)
+    for chrom in native:
+        assert np.array_equal(threaded[chrom].molecules, native[chrom].molecules)
+        assert np.array_equal(threaded[chrom].snp_calls, native[chrom].snp_calls)
     total = 0
     for chrom in python:
         a, b = native[chrom], python[chrom]

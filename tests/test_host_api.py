@@ -117,6 +117,14 @@ def test_compressed_snp_calls_layout_and_growth():
     merged = CompressedSNPCalls.concatenate([c, c])
     assert merged.n_molecules == 10 and merged.n_snp_calls == 30
     assert merged.snp_calls['molecule_index'][15] == 5
+    assert merged.snp_calls.dtype == SNP_CALL_DTYPE and merged.molecules.dtype == MOLECULE_DTYPE
+    assert np.array_equal(merged.molecules, np.concatenate([c.molecules[:5], c.molecules[:5]]))
+    shifted = c.snp_calls[:15].copy()
+    shifted['molecule_index'] += 5
+    assert np.array_equal(merged.snp_calls, np.concatenate([c.snp_calls[:15], shifted]))
+    assert c.snp_calls['molecule_index'][0] == 0  # the parts are left untouched
+    empty = CompressedSNPCalls.concatenate([])
+    assert empty.n_molecules == 0 and empty.n_snp_calls == 0
     c.minimize_memory_footprint()
     assert len(c.snp_calls) == 15 and len(c.molecules) == 5
 
