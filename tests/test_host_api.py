@@ -41,6 +41,33 @@ def test_abi_library_exports_every_declared_symbol(native_lib):
     assert native_lib.dmx_estep_plan_supported(4, 0.0, 1) and not native_lib.dmx_estep_plan_supported(9, 0.0, 1)
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every parameter of every prototype in include/demux_b200.h against the ctypes binding: same count, pointers
+    bound as pointers, integers / floats with the declared width (a mismatch would corrupt the call silently)."""
+    import ctypes as C
+    from demuxalot_b200 import _native
+    header = (ROOT / 'include' / 'demux_b200.h').read_text()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    scalar = {'int32_t': C.c_int32, 'int64_t': C.c_int64, 'int': C.c_int, 'float': C.c_float, 'double': C.c_double}
+    prototypes = re.findall(r'([A-Za-z_][A-Za-z0-9_ ]*?[ *]+)\b(dmx_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', header)
+    assert len(prototypes) == len(_native.SIGNATURES)
+    for restype_text, name, params in prototypes:
+        restype, argtypes = _native.SIGNATURES[name]
+        restype_text = restype_text.strip()
+        if restype_text.endswith('*'):
+            assert restype in (C.c_char_p, C.c_void_p), name
+        else:
+            assert restype is scalar[restype_text], (name, restype_text)
+        params = [p.strip() for p in params.split(',')] if params.strip() not in ('', 'void') else []
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for text, bound in zip(params, argtypes):
+            if '*' in text:
+                assert bound is C.c_void_p or issubclass(bound, C._Pointer), (name, text, bound)
+            else:
+                kind = text.replace('const ', '').split()[0]
+                assert bound is scalar[kind], (name, text, bound)
+
+
 def test_host_gather_of_the_barcode_column(native_lib):
     """dmx_host_gather_cb is a host function (no GPU needed): the compressed_cb column of packed molecule records."""
     import ctypes as C
