@@ -1,7 +1,10 @@
 // Issue-rate microbenchmark shaped like the pair E-step's inner loop (sm_100a): every thread keeps NCH packed
 // running products and applies  prod[c] = prod[c] * (a[c % 4] + b[c / 4])  with operands that keep all values at
 // exactly 1.0 (no denormals / infinities, which distort the older microbench_fp32x2 numbers).
-//   mode 0: FADD2 (scalar operand broadcast by the instruction) + FMUL2     -- the kernel's loop
+//   mode 0: FADD2 (scalar operand broadcast by the instruction) + FMUL2     -- the kernel's loop; the 8 x NCH adds of
+//           an iteration take distinct register pairs (16 packed x 16 scalar operands) so that ptxas cannot merge them (it did in
+//           the version that produced profiles/r01_microbench_packed_tile.log: SASS had 32 FADD2 per 256 FMUL2, so the
+//           mode-0 rates of that log must be scaled by 288 / 512 -- 3.51 -> 1.97 warp-instructions/clk/SM)
 //   mode 1: FMUL2 only            mode 2: FADD2 only            mode 3: scalar FADD + FMUL (2 x NCH chains)
 //   mode 4: FFMA2 only
 // Sweeps warps per SM (one warp per CTA, like the warp pair kernel) and chains per thread.
@@ -22,11 +25,13 @@ __global__ void __launch_bounds__(32) bench(float* out, const float* in, int ite
     float sprod[2 * NCH];
     for (int c = 0; c < NCH; ++c) { prod[c] = pack2(1.f, 1.f); sprod[2 * c] = 1.f; sprod[2 * c + 1] = 1.f; }
     // operands from memory so nothing is constant-folded: a = 0.5, b = 0.5 -> factor 1.0
-    float av[8], bv[8];
-    for (int k = 0; k < 8; ++k) { av[k] = in[k]; bv[k] = in[8 + k]; }
-    const uint64_t a2[4] = {pack2(av[0], av[1]), pack2(av[2], av[3]), pack2(av[4], av[5]), pack2(av[6], av[7])};
-    const uint64_t one2 = pack2(in[16], in[16]);  // 1.0
-    const uint64_t zero2 = pack2(in[17], in[17]);  // 0.0
+    float av[32], bv[16];
+    for (int k = 0; k < 32; ++k) av[k] = in[k];
+    for (int k = 0; k < 16; ++k) bv[k] = in[32 + k];
+    uint64_t a2[16];
+    for (int k = 0; k < 16; ++k) a2[k] = pack2(av[2 * k], av[2 * k + 1]);
+    const uint64_t one2 = pack2(in[48], in[48]);  // 1.0
+    const uint64_t zero2 = pack2(in[49], in[49]);  // 0.0
     long long t0 = clock64();
 #pragma unroll 1
     for (int it = 0; it < iters; ++it) {
@@ -34,7 +39,7 @@ __global__ void __launch_bounds__(32) bench(float* out, const float* in, int ite
         for (int rep = 0; rep < 8; ++rep) {
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
-                if (MODE == 0) prod[c] = mul2(prod[c], add2(a2[c % 4], pack2(bv[(c / 4) % 8], bv[(c / 4) % 8])));
+                if (MODE == 0) prod[c] = mul2(prod[c], add2(a2[(rep * NCH + c) % 16], pack2(bv[((rep * NCH + c) / 16) % 16], bv[((rep * NCH + c) / 16) % 16])));
                 if (MODE == 1) prod[c] = mul2(prod[c], one2);
                 if (MODE == 2) prod[c] = add2(prod[c], zero2);
                 if (MODE == 3) {
@@ -82,9 +87,9 @@ void run(const char* name, int warps_per_sm, int instr_per_chain, int lanes_per_
 }
 
 int main() {
-    float h_in[18];
-    for (int k = 0; k < 16; ++k) h_in[k] = 0.5f;
-    h_in[16] = 1.f; h_in[17] = 0.f;
+    float h_in[50];
+    for (int k = 0; k < 48; ++k) h_in[k] = 0.5f;
+    h_in[48] = 1.f; h_in[49] = 0.f;
     float* d_in; cudaMalloc(&d_in, sizeof(h_in));
     cudaMemcpy(d_in, h_in, sizeof(h_in), cudaMemcpyHostToDevice);
     const int warps[] = {4, 8, 12, 16, 24, 32};
