@@ -19,6 +19,8 @@ ncu --set full --clock-control none --import-source on -k regex:estep_pairs_patc
 python scripts/run_config4_shard.py > gpurun_out/config4_shard.log 2>&1
 python scripts/profile_e2e.py > gpurun_out/profile_e2e.log 2>&1
 python scripts/bench_mstep.py > gpurun_out/bench_mstep.log 2>&1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/microbench_packed_tile scripts/microbench_packed_tile.cu && \
+    scripts/microbench_packed_tile > gpurun_out/microbench_packed_tile.log 2>&1
 (python scripts/sweep_table.py 32 656584; python scripts/sweep_table.py 200 1000000) > gpurun_out/sweep_table.log 2>&1
 python scripts/bench_snp_aggregate.py 0.25 > gpurun_out/bench_snp_aggregate.log 2>&1
 # aggregate_on_snps E-step: tens of ms per launch and ~40 replays -- a tenth of the workload and a generous limit
