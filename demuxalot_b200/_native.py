@@ -49,11 +49,21 @@ SIGNATURES = {
     'dmx_snp_logits': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f64, _f64, _ptr, _i64, _ptr, _i64,
                                  _ptr]),
     'dmx_softmax_rows_f64': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
+    'dmx_barcode_histogram': (C.c_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr]),
+    'dmx_route_calls_workspace_bytes': (_i64, [_i64]),
+    'dmx_route_calls': (C.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i32, _ptr, _i64, _ptr, _ptr, _ptr,
+                                  C.POINTER(_i64), _ptr]),
+    'dmx_comm_unique_id': (C.c_int, [_ptr]),
+    'dmx_comm_init': (C.c_int, [_ptr, _i32, _i32, C.POINTER(_ptr)]),
+    'dmx_comm_destroy': (C.c_int, [_ptr]),
+    'dmx_mstep_allreduce_padded_variants': (_i64, [_i64, _i32]),
+    'dmx_mstep_allreduce': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _f64, _ptr, _ptr, _ptr, _i64, _ptr, _i64,
+                                      _i64, _i64, _i64, _ptr, _ptr, _i32, _i32, _ptr]),
     'dmx_round_f64_to_f32': (C.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i32, _ptr]),
 }
 
-ESTEP_EXACT, ESTEP_FAST = 0, 1
-ABI_VERSION = 3
+ESTEP_EXACT, ESTEP_FAST, ESTEP_AUTO = 0, 1, 2
+ABI_VERSION = 4
 
 
 class NativeError(RuntimeError):

@@ -86,7 +86,12 @@ class BamRecord:
             for op, length in self.cigartuples:
                 if op in _CONSUMES_REFERENCE:
                     span += length
-            self._ref_end = self.reference_start + span if span else -1
+            # htslib's bam_endpos: a CIGAR that consumes no reference (all soft clip / insertion) ends at pos + 1;
+            # None only for reads without a CIGAR (pysam also returns None for unmapped reads)
+            if span:
+                self._ref_end = self.reference_start + span
+            else:
+                self._ref_end = self.reference_start + 1 if len(self.cigartuples) else -1
         return None if self._ref_end < 0 else self._ref_end
 
     @property

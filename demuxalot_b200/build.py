@@ -15,7 +15,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / 'csrc'
 LIB_PATH = CSRC / 'libdemux_b200.so'
 SOURCES = ['api.cu', 'builder.cu', 'table.cu', 'estep.cu', 'estep_pairs.cu', 'estep_pairs_warp.cu', 'mstep.cu',
-           'snp_aggregate.cu']
+           'snp_aggregate.cu', 'comm.cu']
 HEADERS = [CSRC / 'common.cuh', CSRC.parent.parent / 'include' / 'demux_b200.h']
 
 HOST_SRC = CSRC.parent / 'csrc_host' / 'bam_counter.cpp'
@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         if proc.returncode != 0:
             raise RuntimeError(f'nvcc failed on {src}:\n{" ".join(cmd)}\n{out}')
         objects.append(str(obj))
-    link = [nvcc, '-shared', '-o', str(LIB_PATH), *objects, '-gencode', 'arch=compute_100a,code=sm_100a']
+    link = [nvcc, '-shared', '-o', str(LIB_PATH), *objects, '-gencode', 'arch=compute_100a,code=sm_100a', '-ldl']
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         raise RuntimeError(f'link failed:\n{" ".join(link)}\n{res.stdout}')

@@ -193,6 +193,70 @@ __global__ void schedule_keys_kernel(const int64_t* __restrict__ offsets, int64_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// sharded pack: every rank unpacks a slice of the calls, then the matched calls travel to the rank that owns their
+// barcode (contiguous barcode ranges).  Stable: a rank's calls stay in call order inside every destination block, and
+// blocks are received in rank order, so call order is kept inside every chromosome, hence inside every (variant,
+// barcode) group, which is what the ordered products of demux.py:282-283 need.
+// ---------------------------------------------------------------------------------------------------------
+
+// matched calls per barcode (the weight the barcode ranges are balanced by)
+__global__ void barcode_histogram_kernel(const int32_t* __restrict__ variant, const int32_t* __restrict__ cb, int64_t n,
+                                         int64_t n_variants, int64_t n_barcodes, unsigned long long* __restrict__ hist) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = variant[k], b = cb[k];
+        if (v >= 0 && (int64_t)v < n_variants && b >= 0 && (int64_t)b < n_barcodes) atomicAdd(&hist[b], 1ull);
+    }
+}
+
+struct RouteCounters {
+    unsigned long long per_rank[64];
+    unsigned long long n_bad_barcode;
+};
+
+// destination of every call: rank owning its barcode, `world` for calls that are dropped (unmatched)
+__global__ void route_keys_kernel(const int32_t* __restrict__ variant, const int32_t* __restrict__ cb, int64_t n,
+                                  int64_t n_variants, int64_t n_barcodes, const int64_t* __restrict__ cuts, int world,
+                                  uint8_t* __restrict__ keys, uint32_t* __restrict__ idx, RouteCounters* counters) {
+    __shared__ unsigned s_count[65];
+    for (int i = threadIdx.x; i < 65; i += blockDim.x) s_count[i] = 0;
+    __syncthreads();
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = variant[k], b = cb[k];
+        int dest = world;
+        if (v >= 0 && (int64_t)v < n_variants) {
+            if (b >= 0 && (int64_t)b < n_barcodes) {
+                dest = 0;
+                while (dest + 1 < world && (int64_t)b >= cuts[dest + 1]) ++dest;  // world <= 64: a short scan
+                atomicAdd(&s_count[dest], 1u);
+            } else {
+                atomicAdd(&s_count[64], 1u);
+            }
+        }
+        keys[k] = (uint8_t)dest;
+        idx[k] = (uint32_t)k;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 65; i += blockDim.x) {
+        const unsigned c = s_count[i];
+        if (c) atomicAdd(i < 64 ? &counters->per_rank[i] : &counters->n_bad_barcode, (unsigned long long)c);
+    }
+}
+
+__global__ void route_gather_kernel(const uint8_t* __restrict__ keys_sorted, const uint32_t* __restrict__ idx_sorted,
+                                    int64_t n_kept, const int32_t* __restrict__ variant, const int32_t* __restrict__ cb,
+                                    const float* __restrict__ e, const int64_t* __restrict__ cuts,
+                                    int32_t* __restrict__ out_variant, int32_t* __restrict__ out_cb,
+                                    float* __restrict__ out_e) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n_kept; k += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t src = idx_sorted[k];
+        out_variant[k] = variant[src];
+        out_cb[k] = cb[src] - (int32_t)cuts[keys_sorted[k]];  // barcode id local to the owner's range
+        out_e[k] = e[src];
+    }
+}
+
 static int bits_for(int64_t max_value) {  // bits needed to represent values 0..max_value
     int b = 1;
     while ((max_value >> b) != 0) ++b;
@@ -252,6 +316,79 @@ int dmx_unpack_match_calls(const uint8_t* snp_calls_packed, int64_t n_calls, con
         geno_vids_sorted,
         n_variants, out_variant, out_cb, out_e);
     DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+
+int dmx_barcode_histogram(const int32_t* call_variant, const int32_t* call_cb, int64_t n_calls, int64_t n_variants,
+                          int64_t n_barcodes, int64_t* histogram, void* stream) {
+    if (n_calls <= 0) return 0;
+    dmx::barcode_histogram_kernel<<<dmx::grid_for(n_calls, 256), 256, 0, (cudaStream_t)stream>>>(
+        call_variant, call_cb, n_calls, n_variants, n_barcodes, (unsigned long long*)histogram);
+    DMX_LAUNCH_CHECK();
+    return 0;
+}
+
+static int64_t route_layout(int64_t n_calls, size_t* keys_b, size_t* idx_a, size_t* idx_b, size_t* counters,
+                            size_t* cub_temp, size_t* cub_bytes) {
+    const int64_t m = n_calls > 0 ? n_calls : 1;
+    size_t temp = 0;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, temp, (const uint8_t*)nullptr, (uint8_t*)nullptr,
+                                        (const uint32_t*)nullptr, (uint32_t*)nullptr, m, 0, 7) != cudaSuccess)
+        return -1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (size_t)dmx::round_up((int64_t)bytes, 256); return o; };
+    take((size_t)m);  // keys_a at offset 0
+    *keys_b = take((size_t)m);
+    *idx_a = take(4 * (size_t)m);
+    *idx_b = take(4 * (size_t)m);
+    *counters = take(sizeof(dmx::RouteCounters));
+    *cub_temp = take(temp);
+    *cub_bytes = temp;
+    return (int64_t)off;
+}
+
+int64_t dmx_route_calls_workspace_bytes(int64_t n_calls) {
+    size_t a, b, c, d, e, f;
+    return route_layout(n_calls, &a, &b, &c, &d, &e, &f);
+}
+
+int dmx_route_calls(const int32_t* call_variant, const int32_t* call_cb, const float* call_e, int64_t n_calls,
+                    int64_t n_variants, int64_t n_barcodes, const int64_t* cuts, int32_t world, void* workspace,
+                    int64_t workspace_bytes, int32_t* out_variant, int32_t* out_cb, float* out_e, int64_t* h_counts,
+                    void* stream_) {
+    using namespace dmx;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DMX_REQUIRE(world >= 1 && world <= 64, "world size %d outside [1, 64]", (int)world);
+    DMX_REQUIRE(n_calls >= 0 && n_calls < (1ll << 32) - 1, "n_calls out of range");
+    for (int r = 0; r <= world; ++r) h_counts[r] = 0;
+    if (n_calls == 0) return 0;
+    size_t o_keys_b, o_idx_a, o_idx_b, o_counters, o_temp, temp_bytes;
+    const int64_t need = route_layout(n_calls, &o_keys_b, &o_idx_a, &o_idx_b, &o_counters, &o_temp, &temp_bytes);
+    DMX_REQUIRE(need >= 0 && workspace_bytes >= need, "route workspace too small");
+    uint8_t* ws = (uint8_t*)workspace;
+    uint8_t* keys_a = ws;
+    uint8_t* keys_b = ws + o_keys_b;
+    uint32_t* idx_a = (uint32_t*)(ws + o_idx_a);
+    uint32_t* idx_b = (uint32_t*)(ws + o_idx_b);
+    RouteCounters* counters = (RouteCounters*)(ws + o_counters);
+    DMX_CUDA(cudaMemsetAsync(counters, 0, sizeof(RouteCounters), stream));
+    route_keys_kernel<<<grid_for(n_calls, 256), 256, 0, stream>>>(call_variant, call_cb, n_calls, n_variants, n_barcodes,
+                                                                  cuts, world, keys_a, idx_a, counters);
+    DMX_LAUNCH_CHECK();
+    DMX_CUDA(cub::DeviceRadixSort::SortPairs(ws + o_temp, temp_bytes, (const uint8_t*)keys_a, keys_b,
+                                             (const uint32_t*)idx_a, idx_b, n_calls, 0, 7, stream));
+    RouteCounters h;
+    DMX_CUDA(cudaMemcpyAsync(&h, counters, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    DMX_CUDA(cudaStreamSynchronize(stream));
+    h_counts[world] = (int64_t)h.n_bad_barcode;  // the caller raises on every rank (a collective follows)
+    int64_t kept = 0;
+    for (int r = 0; r < world; ++r) { h_counts[r] = (int64_t)h.per_rank[r]; kept += h_counts[r]; }
+    if (kept > 0) {
+        route_gather_kernel<<<grid_for(kept, 256), 256, 0, stream>>>(keys_b, idx_b, kept, call_variant, call_cb, call_e,
+                                                                     cuts, out_variant, out_cb, out_e);
+        DMX_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -35,7 +35,7 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
                             const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
                             const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
                             float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
-                            int64_t ld_logits, double* partial, int64_t n_cols, cudaStream_t stream);
+                            int64_t ld_logits, double* partial, int64_t n_cols, int flavour, cudaStream_t stream);
 float pair_doublet_bonus(int n_genotypes, double dp);
 int launch_plan_segments(const int64_t* offsets, const int32_t* order, int64_t n_barcodes, int seg_rows,
                          int32_t* n_seg, cudaStream_t stream);
@@ -170,7 +170,15 @@ struct CombineParams {
     int64_t ld_prior;
     int n_singlets;
     float doublet_bonus;
+    double scale;  // partial sums are log2-sums (ln 2) or natural-log sums (1)
 };
+
+// DMX_ESTEP_AUTO: the reference's roundings wherever the E-step waits on the row stream and they are (nearly) free --
+// singlet columns only, or at most 8 genotypes -- and the product arithmetic for the FP32-bound pair kernels
+static inline int resolve_flavour(int flavour, int G, double doublet_prior) {
+    if (flavour != DMX_ESTEP_AUTO) return flavour;
+    return (doublet_prior == 0 || G <= 8) ? DMX_ESTEP_EXACT : DMX_ESTEP_FAST;
+}
 
 __global__ void __launch_bounds__(128) softmax_rows_kernel(float* __restrict__ logits, int64_t ld_logits, int n_cols,
                                                            float* __restrict__ post, int64_t ld_post,
@@ -190,7 +198,7 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(float* __restrict__ l
                 double sum = 0.0;
                 for (int k = 0; k < n_seg; ++k) sum += cp.partial[(int64_t)(seg_first + k) * n_cols + c];
                 const float pen = c < cp.n_singlets ? 0.f : cp.doublet_bonus;
-                float logit = (float)((double)pen + sum * 0.693147180559945309417232);
+                float logit = (float)((double)pen + sum * cp.scale);
                 if (cp.prior) logit = (float)((double)logit + cp.prior[barcode * cp.ld_prior + c]);
                 out[c] = logit;
             }
@@ -282,6 +290,7 @@ int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int
 }
 
 int dmx_estep_plan_supported(int32_t n_genotypes, double doublet_prior, int32_t flavour) {
+    flavour = dmx::resolve_flavour(flavour, n_genotypes, doublet_prior);
     if (!dmx::estep_pairs_warp_supported(n_genotypes, flavour)) return 0;
     return (doublet_prior != 0 || n_genotypes <= 8) ? 1 : 0;  // singlets only: the lane-per-row kernel (G <= 8)
 }
@@ -332,7 +341,9 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
     const int G = n_genotypes;
     DMX_REQUIRE(G >= 1, "n_genotypes must be positive");
     DMX_REQUIRE(doublet_prior >= 0 && doublet_prior < 1, "doublet_prior must be in [0, 1)");
-    DMX_REQUIRE(flavour == DMX_ESTEP_EXACT || flavour == DMX_ESTEP_FAST, "unknown E-step flavour %d", flavour);
+    DMX_REQUIRE(flavour == DMX_ESTEP_EXACT || flavour == DMX_ESTEP_FAST || flavour == DMX_ESTEP_AUTO,
+                "unknown E-step flavour %d", flavour);
+    flavour = resolve_flavour(flavour, G, doublet_prior);
     DMX_REQUIRE(ld_table % 4 == 0 && ld_table >= G, "ld_table must be a multiple of 4 and >= n_genotypes");
     DMX_REQUIRE(((uintptr_t)table & 15) == 0, "table must be 16-byte aligned");
     const int64_t n_cols = doublet_prior == 0 ? G : (int64_t)G * (G + 1) / 2;
@@ -370,7 +381,8 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
     } else if (planned) {
         const int rc = launch_estep_pairs_warp(barcode_offsets, barcode_order, seg_prefix, item_slot, n_items, seg_rows,
                                                csr_variant, csr_e, table, ld_table, G, doublet_prior, table_floor,
-                                               prior_logits, ld_prior, out_logits, ld_out, partial, n_cols, stream);
+                                               prior_logits, ld_prior, out_logits, ld_out, partial, n_cols, flavour,
+                                               stream);
         if (rc) return rc;
         if (partial) {
             CombineParams cp;
@@ -381,6 +393,7 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
             cp.ld_prior = ld_prior;
             cp.n_singlets = G;
             cp.doublet_bonus = doublet_prior == 0 ? 0.f : pair_doublet_bonus(G, doublet_prior);
+            cp.scale = flavour == DMX_ESTEP_EXACT ? 1.0 : 0.693147180559945309417232;
             return launch_softmax(out_logits, ld_out, n_barcodes, (int)n_cols, posteriors, ld_post, singlet_posteriors,
                                   ld_singlet, G, stream, &cp);
         }

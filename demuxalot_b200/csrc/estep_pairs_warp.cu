@@ -683,7 +683,10 @@ static bool patch_kernel_supported(int G) {
 // deterministic).  Rows past the end multiply by exactly 1.  Same work items as the other warp kernels.
 // ---------------------------------------------------------------------------------------------------------------
 // SINGLETS: doublet_prior == 0 -- only the G singlet columns, factor a_g itself (no pair sum, no factor 2).
-template <int GT, int FLUSH_ROWS, bool SINGLETS>
+// EXACT: the reference's own roundings (demux.py:188-190, 261): p = fl(fl(P_i + P_j) * 0.5), x = fl(fl(p (1 - e)) + e'),
+// t = logf(x), float64 accumulation -- these widths wait on the row stream, so the per-term log costs little, and the
+// float32 logits then carry the reference's rounding noise instead of an independent one (posterior bar 1e-6).
+template <int GT, int FLUSH_ROWS, bool SINGLETS, bool EXACT>
 __global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsParams p) {
     constexpr int CT = SINGLETS ? GT : GT * (GT + 1) / 2;
     constexpr int WAVES = 4;  // rows in flight per lane
@@ -700,14 +703,19 @@ __global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsPa
     if (row_lo > b_hi) row_lo = b_hi;
     const int64_t row_hi = row_lo + per < b_hi ? row_lo + per : b_hi;
 
-    float prod[CT];
-    int esum[CT];
+    float prod[EXACT ? 1 : CT];
+    int esum[EXACT ? 1 : CT];
+    double acc[EXACT ? CT : 1];
 #pragma unroll
-    for (int c = 0; c < CT; ++c) { prod[c] = 1.f; esum[c] = 0; }
+    for (int c = 0; c < (EXACT ? 1 : CT); ++c) { prod[c] = 1.f; esum[c] = 0; }
+#pragma unroll
+    for (int c = 0; c < (EXACT ? CT : 1); ++c) acc[c] = 0.0;
     int n_flushes = 0, since_flush = 0;
 
     for (int64_t base = row_lo + lane; base < row_hi; base += 32 * WAVES) {  // lanes run out of rows at different times
         float a[WAVES][GT];
+        float w_row[WAVES], ef_row[WAVES];
+        bool ok_row[WAVES];
 #pragma unroll
         for (int u = 0; u < WAVES; ++u) {
             const int64_t row = base + 32 * u;
@@ -716,6 +724,7 @@ __global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsPa
             const float e = ok ? __ldg(p.e + row) : 0.f;
             const float w = __fsub_rn(1.f, e);
             const float ef = fmaxf(e, WARP_ERROR_FLOOR);
+            w_row[u] = w; ef_row[u] = ef; ok_row[u] = ok;
             const float4* src = reinterpret_cast<const float4*>(p.table + (int64_t)v * p.ld_table);
 #pragma unroll
             for (int q = 0; q < (GT + 3) / 4; ++q) {
@@ -724,9 +733,26 @@ __global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsPa
                 const float x4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // rows past the end are neutral: 0.5 + 0.5 = 1 (pairs), 1 (singlets)
-                    if (4 * q + k < GT) a[u][4 * q + k] = ok ? fmaf(x4[k], w, ef) : (SINGLETS ? 1.f : 0.5f);
+                    if (4 * q + k < GT) {
+                        if constexpr (EXACT) a[u][4 * q + k] = x4[k];  // the table entry itself
+                        else a[u][4 * q + k] = ok ? fmaf(x4[k], w, ef) : (SINGLETS ? 1.f : 0.5f);
+                    }
             }
         }
+        if constexpr (EXACT) {
+#pragma unroll
+            for (int u = 0; u < WAVES; ++u) {
+                if (!ok_row[u]) continue;
+                int c = 0;
+#pragma unroll
+                for (int i = 0; i < GT; ++i)
+#pragma unroll
+                    for (int j = i; j < (SINGLETS ? i + 1 : GT); ++j, ++c) {
+                        const float pc = (i == j) ? a[u][i] : __fmul_rn(__fadd_rn(a[u][i], a[u][j]), 0.5f);
+                        acc[c] += (double)logf(__fadd_rn(__fmul_rn(pc, w_row[u]), ef_row[u]));
+                    }
+            }
+        } else {
 #pragma unroll
         for (int u = 0; u < WAVES; ++u) {
             int c = 0;
@@ -740,8 +766,9 @@ __global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsPa
                 }
             }
         }
+        }
         since_flush += WAVES;
-        if (since_flush >= FLUSH_ROWS) {  // lane-local row count: uniform across the warp's active lanes
+        if (!EXACT && since_flush >= FLUSH_ROWS) {  // lane-local row count: uniform across the warp's active lanes
             since_flush = 0;
             ++n_flushes;
 #pragma unroll
@@ -761,15 +788,17 @@ __global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsPa
     for (int i = 0; i < GT; ++i)
 #pragma unroll
         for (int j = i; j < (SINGLETS ? i + 1 : GT); ++j, ++c) {
-            double v = (double)(esum[c] - 127 * n_flushes) + (double)wlg2(prod[c]);
+            double v;
+            if constexpr (EXACT) v = acc[c];  // natural-log sum
+            else v = (double)(esum[c] - 127 * n_flushes) + (double)wlg2(prod[c]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             if (lane == (c & 31) && i < G && j < G) {
-                const double sum = v - real_rows;
+                const double sum = EXACT ? v : v - real_rows;
                 const int64_t col = (i == j) ? i : (int64_t)G + (int64_t)i * G - (int64_t)i * (i + 1) / 2 + (j - i - 1);
                 if (n_seg == 1) {
                     const float pen = (i == j) ? 0.f : p.doublet_bonus;
-                    float logit = (float)((double)pen + sum * 0.693147180559945309417232);
+                    float logit = (float)((double)pen + (EXACT ? sum : sum * 0.693147180559945309417232));
                     if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
                     p.logits[barcode * p.ld_logits + col] = logit;
                 } else {
@@ -832,10 +861,10 @@ float pair_doublet_bonus(int n_genotypes, double dp) {  // demux.py:168-172
 }
 
 bool estep_pairs_warp_supported(int G, int flavour) {
-    if (flavour != DMX_ESTEP_FAST) return false;
     if (warp_env_int("DMX_PAIRS_WARP", 1) == 0) return false;
     const int nb = (G + 7) / 8;
-    if (G <= 8) return warp_env_int("DMX_PAIRS_SMALL", 1) != 0;  // lane-per-row kernel
+    if (G <= 8) return warp_env_int("DMX_PAIRS_SMALL", 1) != 0;  // lane-per-row kernel, both flavours
+    if (flavour != DMX_ESTEP_FAST) return false;
     if (nb == 2) return true;                                    // 3 tiles x 10 row groups
     if (nb == 3 || nb == 4 || nb == 5 || nb == 7) return true;  // lane utilisation >= 28 / 32
     return patch_kernel_supported(G);                            // other widths: estep_pairs.cu
@@ -855,7 +884,7 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
                             const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
                             const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
                             float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
-                            int64_t ld_logits, double* partial, int64_t n_cols, cudaStream_t stream) {
+                            int64_t ld_logits, double* partial, int64_t n_cols, int flavour, cudaStream_t stream) {
     DMX_REQUIRE(seg_rows >= 16 && seg_rows <= 4096, "seg_rows %d outside [16, 4096]", seg_rows);
     DMX_REQUIRE(n_items > 0 && n_items < (1ll << 31), "bad item count %lld", (long long)n_items);
     WarpPairsParams p;
@@ -883,10 +912,14 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
     if (G <= 8) {
         // 16 (8) factors in [2 (floor + 1e-4), 2.0002] per product between flushes, as in the tiled kernels; singlet
         // factors are only >= 1e-4: always 8
-#define DMX_SMALL(GT_)                                                                                        \
-        if (doublet_prior == 0) estep_pairs_small_kernel<GT_, 8, true><<<(unsigned)n_items, 32, 0, stream>>>(p);  \
-        else if (long_products) estep_pairs_small_kernel<GT_, 16, false><<<(unsigned)n_items, 32, 0, stream>>>(p); \
-        else estep_pairs_small_kernel<GT_, 8, false><<<(unsigned)n_items, 32, 0, stream>>>(p)
+#define DMX_SMALL(GT_)                                                                                                \
+        if (flavour == DMX_ESTEP_EXACT) {                                                                             \
+            if (doublet_prior == 0) estep_pairs_small_kernel<GT_, 8, true, true><<<(unsigned)n_items, 32, 0, stream>>>(p); \
+            else estep_pairs_small_kernel<GT_, 8, false, true><<<(unsigned)n_items, 32, 0, stream>>>(p);              \
+        }                                                                                                             \
+        else if (doublet_prior == 0) estep_pairs_small_kernel<GT_, 8, true, false><<<(unsigned)n_items, 32, 0, stream>>>(p);  \
+        else if (long_products) estep_pairs_small_kernel<GT_, 16, false, false><<<(unsigned)n_items, 32, 0, stream>>>(p); \
+        else estep_pairs_small_kernel<GT_, 8, false, false><<<(unsigned)n_items, 32, 0, stream>>>(p)
         if (G <= 2) { DMX_SMALL(2); }
         else if (G <= 4) { DMX_SMALL(4); }
         else { DMX_SMALL(8); }

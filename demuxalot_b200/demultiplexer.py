@@ -141,11 +141,11 @@ class DevicePack:
     n_calls: int
     n_matched: int
     n_rows: int
-    barcode_range: Tuple[int, int]
-    # molecule-level calls in original order (variant == -1: unmatched)
-    call_variant: torch.Tensor
-    call_cb: torch.Tensor
-    call_e: torch.Tensor
+    barcode_range: Tuple[int, int]  # global barcodes [lo, hi) held by this pack; ids below are local (cb - lo)
+    # molecule-level calls in original order (variant == -1: unmatched); None when the caller does not need them
+    call_variant: Optional[torch.Tensor]
+    call_cb: Optional[torch.Tensor]
+    call_e: Optional[torch.Tensor]
     # rows, reference order (variant-major) -- M-step
     csc_variant: torch.Tensor
     csc_cb: torch.Tensor
@@ -187,7 +187,7 @@ class Demultiplexer:
     compensation_during_computing_barcode_logits = 0.5
 
     # B200-specific knobs (not in the reference)
-    estep_flavour = 'fast'  # 'fast' | 'exact', see include/demux_b200.h DMX_ESTEP_*
+    estep_flavour = 'auto'  # 'auto' | 'fast' | 'exact', see include/demux_b200.h DMX_ESTEP_*
     device: Optional[torch.device] = None  # None -> current CUDA device
     process_group = None  # torch.distributed group for barcode-sharded / multi-lane EM (see distributed.py)
     schedule_barcodes = True  # launch the deepest barcodes first (dmx_barcode_schedule)
@@ -204,8 +204,11 @@ class Demultiplexer:
     # variant-range tiles of the sharded M-step: all-reduce of tile k overlaps the M-step of tile k + 1.  Measured
     # (profiles/r01_allreduce_sweep_*.json): the 168 MB all-reduce is 0.34 ms over NVLink, every extra tile costs
     # ~0.25 ms of stream hand-over, so one tile wins; more tiles only pay off for tables of many GB.
-    mstep_allreduce_tiles = 1
-    mstep_allreduce_dtype = 'float64'  # 'float64': rounded once after the global sum; 'float32': half the bytes
+    mstep_allreduce_tiles = 2
+    # 'float64': reduce-scatter of float64 partials, one rounding after the global sum (N GPUs give the bits of one up
+    # to float64 regrouping), all-gather of float32; 'float32': float32 all-reduce, half the bytes again at the price of
+    # one rounding per shard (~world_size * 6e-8 relative on the addition, far inside the 1e-5 parity bar)
+    mstep_allreduce_dtype = 'float64'
 
     # ------------------------------------------------------------------------------------------------ helpers
     @classmethod
@@ -215,7 +218,7 @@ class Demultiplexer:
 
     @classmethod
     def _flavour(cls) -> int:
-        return {'fast': _native.ESTEP_FAST, 'exact': _native.ESTEP_EXACT}[cls.estep_flavour]
+        return {'fast': _native.ESTEP_FAST, 'exact': _native.ESTEP_EXACT, 'auto': _native.ESTEP_AUTO}[cls.estep_flavour]
 
     @staticmethod
     def _doublet_penalties(n_genotypes: int, doublet_prior: float) -> np.ndarray:
@@ -229,165 +232,323 @@ class Demultiplexer:
         return out
 
     # ------------------------------------------------------------------------------------------------ pack
+    @staticmethod
+    def _genotype_index(genotypes) -> dict:
+        return genotypes.hot_path_index() if hasattr(genotypes, 'hot_path_index') else _foreign_hot_index(genotypes)
+
+    @staticmethod
+    def _select_parts(chromosome2compressed_snp_calls, chrom2id) -> list:
+        """[(chrom_id, calls)] of the chromosomes that carry calls, in dict order (demux.py:334)."""
+        parts = []
+        for chrom, calls in chromosome2compressed_snp_calls.items():
+            if chrom not in chrom2id:
+                # demux.py:339-341 skips the chromosome and the counter check at :359 then fails
+                assert calls.n_snp_calls == 0, \
+                    f'calls on chromosome {chrom!r}, which is absent from the genotypes'
+                continue
+            if calls.n_snp_calls:
+                parts.append((chrom2id[chrom], calls))
+        return parts
+
     @classmethod
-    def _pack_device(cls, chromosome2compressed_snp_calls, genotypes, n_barcodes: int, add_data_prior: bool,
-                     barcode_range: Optional[Tuple[int, int]] = None) -> DevicePack:
-        """Device version of pack_calls (demux.py:302-392)."""
+    def _upload_unpack(cls, parts, dindex, n_variants: int, dev, shard=None):
+        """
+        (a2) Uploads the packed records and matches them against the genotype keys (demux.py:334-358):
+        returns (call_variant, call_cb, call_e, n_calls), device SoA over the calls this process handles, in call
+        order.  `shard` = (rank, world, group): this rank takes the rank-th contiguous slice of every chromosome's
+        calls (1 / world of the bytes cross its PCIe link); the compressed_cb column of the molecules is uploaded in
+        slices as well and all-gathered over NVLink, since a call may point at any molecule.
+        """
         lib = _native.load()
-        dev = cls._device()
-        index = genotypes.hot_path_index() if hasattr(genotypes, 'hot_path_index') else _foreign_hot_index(genotypes)
-        n_variants, n_genotypes = genotypes.n_variants, genotypes.n_genotypes
-        raw = np.asarray(genotypes.get_betas())
-        assert raw.dtype == np.float32 and raw.shape == (n_variants, n_genotypes)
+        stream = _stream()
+        main = torch.cuda.current_stream()
+        copy_stream = _copy_stream(dev) if cls.pipelined_upload else main
+        gkeys, gvids = dindex['keys_sorted'], dindex['vids_sorted']
+        rank, world, group = shard if shard is not None else (0, 1, None)
 
-        with torch.cuda.device(dev):
-            stream = _stream()
-            main = torch.cuda.current_stream()
-            copy_stream = _copy_stream(dev) if cls.pipelined_upload else main
-            dindex = _device_index(index, dev)
-            gkeys, gvids = dindex['keys_sorted'], dindex['vids_sorted']
-            snp_offsets, snp_variants = dindex['snp_offsets'], dindex['snp_variants']
+        def call_slice(n):
+            return (n * rank // world, n * (rank + 1) // world)
 
-            chrom2id = index['chrom2id']
-            parts = []
-            for chrom, calls in chromosome2compressed_snp_calls.items():
-                if chrom not in chrom2id:
-                    # demux.py:339-341 skips the chromosome and the counter check at :359 then fails
-                    assert calls.n_snp_calls == 0, \
-                        f'calls on chromosome {chrom!r}, which is absent from the genotypes'
-                    continue
-                if calls.n_snp_calls:
-                    parts.append((chrom2id[chrom], calls))
-            n_calls = sum(c.n_snp_calls for _cid, c in parts)
-            call_variant = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
-            call_cb = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
-            call_e = torch.empty(max(n_calls, 1), dtype=torch.float32, device=dev)
-            # All uploads are queued on the copy stream up front (chromosome records, then the betas); the unpack
-            # kernel of chromosome k runs on the main stream while chromosome k + 1 is still on the wire, and the
-            # row builder overlaps the upload of the betas.
-            gather = cls.host_gather_threads > 0 and len(parts) > 0
-            staging = ready_flags = worker = None
-            molecule_arrays = [_as_dtype(c.molecules[:c.n_molecules], MOLECULE_DTYPE) for _cid, c in parts]
-            # one packing call at a time fills the per-device staging buffer and queues the uploads out of it
-            with (_CB_STAGING_LOCK if gather else contextlib.nullcontext()):
-                if gather:
-                    n_mols = [c.n_molecules for _cid, c in parts]
-                    staging = _cb_staging(dev, sum(n_mols))
-                    if staging['last_read'] is not None:
-                        staging['last_read'].synchronize()  # the previous call's upload out of this buffer is done
-                    ready_flags = [threading.Event() for _ in parts]
-                    base_ptr, n_threads = staging['buffer'].data_ptr(), int(cls.host_gather_threads)
+        def molecule_slice(n):  # equal slices (all_gather_into_tensor), the last ones possibly short or empty
+            per = -(-n // world) if n else 0
+            return min(rank * per, n), min((rank + 1) * per, n), per
 
-                    def gather_all():  # ctypes releases the GIL: runs beside the upload submissions below
-                        offset = 0
-                        for k, mols in enumerate(molecule_arrays):
-                            rc = -1  # whatever happens the flag is set, so the consumer below never waits for ever
-                            try:
-                                rc = lib.dmx_host_gather_cb(mols.ctypes.data, len(mols), base_ptr + 4 * offset, n_threads)
-                            finally:
-                                ready_flags[k].rc = rc
-                                ready_flags[k].set()
-                            offset += len(mols)
+        call_ranges = [call_slice(c.n_snp_calls) for _cid, c in parts]
+        n_calls = sum(hi - lo for lo, hi in call_ranges)
+        call_variant = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
+        call_cb = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
+        call_e = torch.empty(max(n_calls, 1), dtype=torch.float32, device=dev)
+        # All uploads are queued on the copy stream up front; the unpack kernel of chromosome k runs on the main
+        # stream while chromosome k + 1 is still on the wire.
+        gather = (cls.host_gather_threads > 0 or world > 1) and len(parts) > 0
+        staging = ready_flags = worker = None
+        molecule_arrays = [_as_dtype(c.molecules[:c.n_molecules], MOLECULE_DTYPE) for _cid, c in parts]
+        mol_ranges = [molecule_slice(len(m)) for m in molecule_arrays]
+        # one packing call at a time fills the per-device staging buffer and queues the uploads out of it
+        with (_CB_STAGING_LOCK if gather else contextlib.nullcontext()):
+            if gather:
+                staging = _cb_staging(dev, sum(hi - lo for lo, hi, _per in mol_ranges))
+                if staging['last_read'] is not None:
+                    staging['last_read'].synchronize()  # the previous call's upload out of this buffer is done
+                ready_flags = [threading.Event() for _ in parts]
+                base_ptr, n_threads = staging['buffer'].data_ptr(), max(1, int(cls.host_gather_threads))
 
-                    worker = threading.Thread(target=gather_all, daemon=True)
-                    worker.start()
-                uploads = []
-                for (cid, calls), molecules in zip(parts, molecule_arrays):
-                    snp_calls = _as_dtype(calls.snp_calls[:calls.n_snp_calls], SNP_CALL_DTYPE)
-                    d_calls, ready = _upload_async(snp_calls, dev, copy_stream)
-                    d_mols = None
-                    if not gather:
-                        d_mols, ready = _upload_async(molecules, dev, copy_stream)
-                    uploads.append([cid, calls, d_calls, d_mols, ready])
-                if gather:  # the compact columns follow the call records on the wire, in the order the gathers finish
+                def gather_all():  # ctypes releases the GIL: runs beside the upload submissions below
                     offset = 0
-                    for k, entry in enumerate(uploads):
-                        ready_flags[k].wait()
-                        _native.check(ready_flags[k].rc, 'dmx_host_gather_cb')
-                        n = entry[1].n_molecules
-                        with torch.cuda.stream(copy_stream):
-                            d_cb = staging['buffer'][offset:offset + n].to(dev, non_blocking=True)
-                            event = torch.cuda.Event()
-                            event.record(copy_stream)
-                        d_cb.record_stream(main)
-                        entry[3], entry[4] = d_cb, event
-                        staging['last_read'] = event
-                        offset += n
-                    worker.join()
-            if raw.size:
-                raw_dev, raw_ready = _upload_async(raw, dev, copy_stream)
-            else:
-                raw_dev, raw_ready = torch.empty((n_variants, n_genotypes), device=dev), None
-            done = 0
-            for cid, calls, d_calls, d_mols, ready in uploads:
-                main.wait_event(ready)
-                n = calls.n_snp_calls
+                    for k, (mols, (lo, hi, _per)) in enumerate(zip(molecule_arrays, mol_ranges)):
+                        rc = -1  # whatever happens the flag is set, so the consumer below never waits for ever
+                        try:
+                            rc = lib.dmx_host_gather_cb(mols[lo:hi].ctypes.data, hi - lo, base_ptr + 4 * offset, n_threads)
+                        finally:
+                            ready_flags[k].rc = rc
+                            ready_flags[k].set()
+                        offset += hi - lo
+
+                worker = threading.Thread(target=gather_all, daemon=True)
+                worker.start()
+            uploads = []
+            for (cid, calls), molecules, (k_lo, k_hi) in zip(parts, molecule_arrays, call_ranges):
+                snp_calls = _as_dtype(calls.snp_calls[:calls.n_snp_calls], SNP_CALL_DTYPE)[k_lo:k_hi]
+                d_calls, ready = _upload_async(snp_calls, dev, copy_stream)
+                d_mols = None
+                if not gather:
+                    d_mols, ready = _upload_async(molecules, dev, copy_stream)
+                uploads.append([cid, k_hi - k_lo, d_calls, d_mols, len(molecules), ready])
+            if gather:  # the compact columns follow the call records on the wire, in the order the gathers finish
+                offset = 0
+                for k, entry in enumerate(uploads):
+                    ready_flags[k].wait()
+                    _native.check(ready_flags[k].rc, 'dmx_host_gather_cb')
+                    lo, hi, per = mol_ranges[k]
+                    with torch.cuda.stream(copy_stream):
+                        if world > 1:  # equal-sized slices: the tail of the last ones is never read
+                            d_cb = torch.zeros(max(per, 1), dtype=torch.int32, device=dev)
+                            d_cb[:hi - lo].copy_(staging['buffer'][offset:offset + hi - lo], non_blocking=True)
+                        else:
+                            d_cb = staging['buffer'][offset:offset + hi - lo].to(dev, non_blocking=True)
+                        event = torch.cuda.Event()
+                        event.record(copy_stream)
+                    d_cb.record_stream(main)
+                    entry[3], entry[5] = d_cb, event
+                    staging['last_read'] = event
+                    offset += hi - lo
+                worker.join()
+        done = 0
+        for (cid, n, d_calls, d_mols, n_molecules, ready), (_lo, _hi, per) in zip(uploads, mol_ranges):
+            main.wait_event(ready)
+            if world > 1:
+                import torch.distributed as dist
+                full = torch.empty(max(per, 1) * world, dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(full, d_mols, group=group)
+                d_mols = full
+            if n:
                 _native.check(lib.dmx_unpack_match_calls(
-                    d_calls.data_ptr(), n, d_mols.data_ptr(), calls.n_molecules, 4 if gather else 12, cid,
+                    d_calls.data_ptr(), n, d_mols.data_ptr(), n_molecules, 4 if gather else 12, cid,
                     gkeys.data_ptr(), gvids.data_ptr(), n_variants,
                     call_variant[done:].data_ptr(), call_cb[done:].data_ptr(), call_e[done:].data_ptr(), stream),
                     'dmx_unpack_match_calls')
-                done += n
-            del uploads  # the record buffers return to the allocator once the kernels that read them are done
+            done += n
+        del uploads  # the record buffers return to the allocator once the kernels that read them are done
+        return call_variant, call_cb, call_e, n_calls
 
-            lo, hi = (0, n_barcodes) if barcode_range is None else barcode_range
-            ws_bytes = lib.dmx_build_rows_workspace_bytes(n_calls, n_variants, n_barcodes)
-            if ws_bytes < 0:
-                _native.check(-1, 'dmx_build_rows_workspace_bytes')
-            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            cap = max(n_calls, 1)
-            i32 = dict(dtype=torch.int32, device=dev)
-            csc_variant, csc_cb, csc_count = (torch.empty(cap, **i32) for _ in range(3))
-            csr_variant, csr_row = (torch.empty(cap, **i32) for _ in range(2))
-            csc_e = torch.empty(cap, dtype=torch.float32, device=dev)
-            csr_e = torch.empty(cap, dtype=torch.float32, device=dev)
-            variant_offsets = torch.empty(n_variants + 1, dtype=torch.int64, device=dev)
-            barcode_offsets = torch.empty(n_barcodes + 1, dtype=torch.int64, device=dev)
-            n_mol = torch.zeros(max(n_variants, 1), dtype=torch.int64, device=dev)  # filled only for the data prior
-            h_rows, h_matched = C.c_int64(0), C.c_int64(0)
-            _native.check(lib.dmx_build_rows(
-                call_variant.data_ptr(), call_cb.data_ptr(), call_e.data_ptr(), n_calls, n_variants, n_barcodes,
-                lo, hi, workspace.data_ptr(), ws_bytes,
-                csc_variant.data_ptr(), csc_cb.data_ptr(), csc_e.data_ptr(), csc_count.data_ptr(),
-                variant_offsets.data_ptr(), csr_variant.data_ptr(), csr_e.data_ptr(), csr_row.data_ptr(),
-                barcode_offsets.data_ptr(), n_mol.data_ptr() if add_data_prior else 0, C.byref(h_rows),
-                C.byref(h_matched), stream),
-                'dmx_build_rows')
-            del workspace
-            n_rows = int(h_rows.value)
-            barcode_order = torch.empty(max(n_barcodes, 1), dtype=torch.int32, device=dev)
-            sched_bytes = lib.dmx_barcode_schedule_workspace_bytes(n_barcodes)
-            sched_ws = torch.empty(max(sched_bytes, 1), dtype=torch.uint8, device=dev)
-            _native.check(lib.dmx_barcode_schedule(barcode_offsets.data_ptr(), n_barcodes, barcode_order.data_ptr(),
-                                                   sched_ws.data_ptr(), sched_bytes, stream), 'dmx_barcode_schedule')
+    @classmethod
+    def _unpack_device_parts(cls, device_parts, dindex, chrom2id, n_variants: int, dev):
+        """(a2) for inputs that already sit in device memory: device_parts = [dict(chromosome, records uint8 [n, 13],
+        molecule_cb int32 [n_molecules], n_calls)] (what the uploads of _upload_unpack leave behind)."""
+        lib = _native.load()
+        n_calls = sum(int(p['n_calls']) for p in device_parts)
+        call_variant = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
+        call_cb = torch.empty(max(n_calls, 1), dtype=torch.int32, device=dev)
+        call_e = torch.empty(max(n_calls, 1), dtype=torch.float32, device=dev)
+        done = 0
+        for part in device_parts:
+            n = int(part['n_calls'])
+            if n:
+                _native.check(lib.dmx_unpack_match_calls(
+                    part['records'].data_ptr(), n, part['molecule_cb'].data_ptr(), part['molecule_cb'].numel(), 4,
+                    chrom2id[part['chromosome']], dindex['keys_sorted'].data_ptr(), dindex['vids_sorted'].data_ptr(),
+                    n_variants, call_variant[done:].data_ptr(), call_cb[done:].data_ptr(), call_e[done:].data_ptr(),
+                    _stream()), 'dmx_unpack_match_calls')
+            done += n
+        return call_variant, call_cb, call_e, n_calls
 
-            if add_data_prior and cls.process_group is not None:
-                # multi-lane / sharded EM: the data prior counts molecules of every rank (demux.py:381)
-                import torch.distributed as dist
-                dist.all_reduce(n_mol, op=dist.ReduceOp.SUM, group=cls.process_group)
+    @classmethod
+    def _route_calls(cls, call_variant, call_cb, call_e, n_calls: int, n_variants: int, n_barcodes: int, shard, dev):
+        """
+        Sharded pack, step 2: contiguous barcode ranges balanced by matched calls (histogram all-reduced over the
+        ranks), stable partition of this rank's matched calls by owner (dmx_route_calls) and one all-to-all over
+        NVLink.  Returns (call_variant, call_cb LOCAL to the range, call_e, n_calls, (lo, hi)) of this rank's shard,
+        call order kept inside every chromosome.
+        """
+        import torch.distributed as dist
+        from .distributed import exchange_calls, plan_barcode_shards
+        lib = _native.load()
+        rank, world, group = shard
+        histogram = torch.zeros(max(n_barcodes, 1), dtype=torch.int64, device=dev)
+        _native.check(lib.dmx_barcode_histogram(call_variant.data_ptr(), call_cb.data_ptr(), n_calls, n_variants,
+                                                n_barcodes, histogram.data_ptr(), _stream()), 'dmx_barcode_histogram')
+        dist.all_reduce(histogram, op=dist.ReduceOp.SUM, group=group)
+        ranges = plan_barcode_shards(histogram[:n_barcodes].cpu().numpy(), world)  # identical on every rank
+        cuts = torch.tensor([r[0] for r in ranges] + [n_barcodes], dtype=torch.int64, device=dev)
+        ws_bytes = lib.dmx_route_calls_workspace_bytes(n_calls)
+        if ws_bytes < 0:
+            _native.check(-1, 'dmx_route_calls_workspace_bytes')
+        workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        send = [torch.empty(max(n_calls, 1), dtype=dt, device=dev) for dt in (torch.int32, torch.int32, torch.float32)]
+        h_counts = (C.c_int64 * (world + 1))()
+        _native.check(lib.dmx_route_calls(
+            call_variant.data_ptr(), call_cb.data_ptr(), call_e.data_ptr(), n_calls, n_variants, n_barcodes,
+            cuts.data_ptr(), world, workspace.data_ptr(), ws_bytes, send[0].data_ptr(), send[1].data_ptr(),
+            send[2].data_ptr(), h_counts, _stream()), 'dmx_route_calls')
+        del workspace
+        counts = [int(c) for c in h_counts]
+        received, n_received, n_bad = exchange_calls(send, counts[:world], counts[world], group, dev)
+        # the reference would index past its per-barcode arrays: an input error, raised on every rank
+        assert n_bad == 0, f'{n_bad} matched calls carry a compressed_cb outside [0, n_barcodes={n_barcodes})'
+        return received[0], received[1], received[2], n_received, ranges[rank]
 
-            if raw_ready is not None:
-                main.wait_event(raw_ready)
-            betas_min = raw_dev.min() if raw.size else None  # demux.py:374, asserted by DevicePack.check()
-            betas = torch.empty((n_variants, n_genotypes), dtype=torch.float32, device=dev)
-            scratch = torch.empty(max(n_variants, 1), dtype=torch.float32, device=dev)
-            _native.check(lib.dmx_prior_betas(
-                raw_dev.data_ptr(), n_genotypes, n_variants, n_genotypes, snp_offsets.data_ptr(),
-                snp_variants.data_ptr(), index['n_snps'], n_mol.data_ptr() if add_data_prior else 0,
-                float(genotypes.default_prior), scratch.data_ptr(), betas.data_ptr(), n_genotypes, stream),
-                'dmx_prior_betas')
+    @classmethod
+    def _keep_barcode_range(cls, call_variant, call_cb, call_e, n_calls: int, n_variants: int, n_barcodes: int,
+                            barcode_range: Tuple[int, int], dev):
+        """Single-process restriction to the barcodes [lo, hi): the routing step of the sharded pack with three
+        destinations (below / inside / above the range), of which the middle block is kept -- matched calls of the
+        range in call order, barcode ids local to it."""
+        lib = _native.load()
+        lo, hi = barcode_range
+        assert 0 <= lo <= hi <= n_barcodes
+        cuts = torch.tensor([0, lo, hi, n_barcodes], dtype=torch.int64, device=dev)
+        ws_bytes = lib.dmx_route_calls_workspace_bytes(n_calls)
+        workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        out = [torch.empty(max(n_calls, 1), dtype=dt, device=dev) for dt in (torch.int32, torch.int32, torch.float32)]
+        h_counts = (C.c_int64 * 4)()
+        _native.check(lib.dmx_route_calls(
+            call_variant.data_ptr(), call_cb.data_ptr(), call_e.data_ptr(), n_calls, n_variants, n_barcodes,
+            cuts.data_ptr(), 3, workspace.data_ptr(), ws_bytes, out[0].data_ptr(), out[1].data_ptr(),
+            out[2].data_ptr(), h_counts, _stream()), 'dmx_route_calls')
+        assert h_counts[3] == 0, f'{h_counts[3]} matched calls carry a compressed_cb outside [0, n_barcodes={n_barcodes})'
+        first, n = int(h_counts[0]), int(h_counts[1])
+        return tuple(t[first:first + max(n, 1)] for t in out) + (n,)
+
+    @classmethod
+    def _finish_pack(cls, call_variant, call_cb, call_e, n_calls: int, genotypes, index, dindex, n_barcodes: int,
+                     add_data_prior: bool, dev, barcode_range: Tuple[int, int]) -> DevicePack:
+        """(a3) + (a4): rows in both orders, schedule, regularised betas (demux.py:276-300, 362-390)."""
+        lib = _native.load()
+        stream = _stream()
+        main = torch.cuda.current_stream()
+        n_variants, n_genotypes = genotypes.n_variants, genotypes.n_genotypes
+        raw = np.asarray(genotypes.get_betas())
+        assert raw.dtype == np.float32 and raw.shape == (n_variants, n_genotypes)
+        snp_offsets, snp_variants = dindex['snp_offsets'], dindex['snp_variants']
+        if raw.size:
+            raw_dev, raw_ready = _upload_async(raw, dev, _copy_stream(dev) if cls.pipelined_upload else main)
+        else:
+            raw_dev, raw_ready = torch.empty((n_variants, n_genotypes), device=dev), None
+
+        ws_bytes = lib.dmx_build_rows_workspace_bytes(n_calls, n_variants, n_barcodes)
+        if ws_bytes < 0:
+            _native.check(-1, 'dmx_build_rows_workspace_bytes')
+        workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        cap = max(n_calls, 1)
+        i32 = dict(dtype=torch.int32, device=dev)
+        csc_variant, csc_cb, csc_count = (torch.empty(cap, **i32) for _ in range(3))
+        csr_variant, csr_row = (torch.empty(cap, **i32) for _ in range(2))
+        csc_e = torch.empty(cap, dtype=torch.float32, device=dev)
+        csr_e = torch.empty(cap, dtype=torch.float32, device=dev)
+        variant_offsets = torch.empty(n_variants + 1, dtype=torch.int64, device=dev)
+        barcode_offsets = torch.empty(n_barcodes + 1, dtype=torch.int64, device=dev)
+        n_mol = torch.zeros(max(n_variants, 1), dtype=torch.int64, device=dev)  # filled only for the data prior
+        h_rows, h_matched = C.c_int64(0), C.c_int64(0)
+        _native.check(lib.dmx_build_rows(
+            call_variant.data_ptr(), call_cb.data_ptr(), call_e.data_ptr(), n_calls, n_variants, n_barcodes,
+            0, n_barcodes, workspace.data_ptr(), ws_bytes,
+            csc_variant.data_ptr(), csc_cb.data_ptr(), csc_e.data_ptr(), csc_count.data_ptr(),
+            variant_offsets.data_ptr(), csr_variant.data_ptr(), csr_e.data_ptr(), csr_row.data_ptr(),
+            barcode_offsets.data_ptr(), n_mol.data_ptr() if add_data_prior else 0, C.byref(h_rows),
+            C.byref(h_matched), stream),
+            'dmx_build_rows')
+        del workspace
+        n_rows = int(h_rows.value)
+
+        def fit(t):  # rows are usually ~60 % of the calls: give the rest of the allocation back
+            return t[:n_rows].clone() if n_rows < 0.9 * cap and cap > (1 << 22) else t[:n_rows]
+
+        csc_variant, csc_cb, csc_count, csc_e, csr_variant, csr_row, csr_e = (
+            fit(t) for t in (csc_variant, csc_cb, csc_count, csc_e, csr_variant, csr_row, csr_e))
+        barcode_order = torch.empty(max(n_barcodes, 1), dtype=torch.int32, device=dev)
+        sched_bytes = lib.dmx_barcode_schedule_workspace_bytes(n_barcodes)
+        sched_ws = torch.empty(max(sched_bytes, 1), dtype=torch.uint8, device=dev)
+        _native.check(lib.dmx_barcode_schedule(barcode_offsets.data_ptr(), n_barcodes, barcode_order.data_ptr(),
+                                               sched_ws.data_ptr(), sched_bytes, stream), 'dmx_barcode_schedule')
+
+        if add_data_prior and cls.process_group is not None:
+            # multi-lane / sharded EM: the data prior counts the molecules of every rank (demux.py:381)
+            import torch.distributed as dist
+            dist.all_reduce(n_mol, op=dist.ReduceOp.SUM, group=cls.process_group)
+
+        if raw_ready is not None:
+            main.wait_event(raw_ready)
+        betas = torch.empty((n_variants, n_genotypes), dtype=torch.float32, device=dev)
+        scratch = torch.empty(max(n_variants, 1), dtype=torch.float32, device=dev)
+        _native.check(lib.dmx_prior_betas(
+            raw_dev.data_ptr(), n_genotypes, n_variants, n_genotypes, snp_offsets.data_ptr(),
+            snp_variants.data_ptr(), index['n_snps'], n_mol.data_ptr() if add_data_prior else 0,
+            float(genotypes.default_prior), scratch.data_ptr(), betas.data_ptr(), n_genotypes, stream),
+            'dmx_prior_betas')
+        betas_min = raw_dev.min() if raw.size else None  # demux.py:374, asserted by DevicePack.check()
 
         return DevicePack(
             device=dev, n_barcodes=n_barcodes, n_variants=n_variants, n_genotypes=n_genotypes,
             n_snps=index['n_snps'], n_calls=n_calls, n_matched=int(h_matched.value), n_rows=n_rows,
-            barcode_range=(lo, hi),
+            barcode_range=barcode_range,
             call_variant=call_variant[:n_calls], call_cb=call_cb[:n_calls], call_e=call_e[:n_calls],
-            csc_variant=csc_variant[:n_rows], csc_cb=csc_cb[:n_rows], csc_e=csc_e[:n_rows],
-            csc_count=csc_count[:n_rows], variant_offsets=variant_offsets,
-            csr_variant=csr_variant[:n_rows], csr_e=csr_e[:n_rows], csr_row=csr_row[:n_rows],
-            barcode_offsets=barcode_offsets, barcode_order=barcode_order[:n_barcodes], n_mol=n_mol[:n_variants], snp_offsets=snp_offsets,
-            snp_variants=snp_variants, variant2snp=index['variant2snp'], raw_betas=raw_dev, betas=betas,
-            betas_min=betas_min)
+            csc_variant=csc_variant, csc_cb=csc_cb, csc_e=csc_e, csc_count=csc_count, variant_offsets=variant_offsets,
+            csr_variant=csr_variant, csr_e=csr_e, csr_row=csr_row,
+            barcode_offsets=barcode_offsets, barcode_order=barcode_order[:n_barcodes], n_mol=n_mol[:n_variants],
+            snp_offsets=snp_offsets, snp_variants=snp_variants, variant2snp=index['variant2snp'], raw_betas=raw_dev,
+            betas=betas, betas_min=betas_min)
+
+    @classmethod
+    def _pack_device(cls, chromosome2compressed_snp_calls, genotypes, n_barcodes: int, add_data_prior: bool,
+                     shard=None, device_parts=None, keep_calls: bool = True,
+                     barcode_range: Optional[Tuple[int, int]] = None) -> DevicePack:
+        """
+        Device version of pack_calls (demux.py:302-392).
+        shard = (rank, world, group): barcode-sharded pack -- this rank uploads a slice of the calls, the matched
+        calls are exchanged, and the returned pack holds the barcodes [lo, hi) = pack.barcode_range with LOCAL
+        barcode ids 0 .. hi - lo (pack.n_barcodes = hi - lo).
+        device_parts: inputs already resident on the device (see _unpack_device_parts) instead of host records; with
+        `shard` they are this rank's share of the calls (any subset).
+        barcode_range = (lo, hi): single-process version of a shard -- only the barcodes [lo, hi) are kept, with local
+        ids (what one rank of a sharded run holds, except that the data prior only counts this range's molecules).
+        """
+        dev = cls._device()
+        index = cls._genotype_index(genotypes)
+        n_variants = genotypes.n_variants
+        with torch.cuda.device(dev):
+            dindex = _device_index(index, dev)
+            if device_parts is not None:
+                call_variant, call_cb, call_e, n_calls = cls._unpack_device_parts(
+                    device_parts, dindex, index['chrom2id'], n_variants, dev)
+            else:
+                parts = cls._select_parts(chromosome2compressed_snp_calls, index['chrom2id'])
+                call_variant, call_cb, call_e, n_calls = cls._upload_unpack(parts, dindex, n_variants, dev, shard)
+            if barcode_range is not None:
+                assert shard is None
+                call_variant, call_cb, call_e, n_calls = cls._keep_barcode_range(
+                    call_variant, call_cb, call_e, n_calls, n_variants, n_barcodes, barcode_range, dev)
+                n_barcodes = barcode_range[1] - barcode_range[0]
+            else:
+                barcode_range = (0, n_barcodes)
+            if shard is not None:
+                call_variant, call_cb, call_e, n_calls, barcode_range = cls._route_calls(
+                    call_variant, call_cb, call_e, n_calls, n_variants, n_barcodes, shard, dev)
+                n_barcodes = barcode_range[1] - barcode_range[0]
+            pack = cls._finish_pack(call_variant, call_cb, call_e, n_calls, genotypes, index, dindex, n_barcodes,
+                                    add_data_prior, dev, barcode_range)
+            if not keep_calls:  # only pack_calls() and the aggregate_on_snps branch read the molecule-level calls
+                pack.call_variant = pack.call_cb = pack.call_e = None
+        return pack
 
     @classmethod
     def pack_calls(cls, chromosome2compressed_snp_calls, genotypes, add_data_prior: bool, n_barcodes: int = None):
@@ -536,60 +697,84 @@ class Demultiplexer:
         return cached
 
     @classmethod
+    def _mstep_buffers(cls, pack: DevicePack) -> dict:
+        """Output buffers of the (sharded) M-step: two float32 [v_pad, G] tables that alternate as `genotype_addition`
+        (v_pad = V rounded up to the world size, padding rows zero) and the float64 partials of the wide wire format."""
+        dev = pack.device
+        world = 1
+        if cls.process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(cls.process_group)
+        v_pad = -(-max(pack.n_variants, 1) // world) * world
+        G = pack.n_genotypes
+        out = {'v_pad': v_pad, 'world': world,
+               'tables': [torch.zeros((v_pad, G), dtype=torch.float32, device=dev) for _ in range(2)]}
+        if world > 1 and cls.mstep_allreduce_dtype == 'float64':
+            n_tiles = max(1, int(cls.mstep_allreduce_tiles))
+            out['partial64'] = torch.zeros((v_pad, G), dtype=torch.float64, device=dev)
+            out['slice64'] = torch.empty((-(-v_pad // n_tiles) + world) * G // world + G, dtype=torch.float64, device=dev)
+        return out
+
+    @classmethod
     def _m_step(cls, pack: DevicePack, singlets: torch.Tensor, out: Optional[torch.Tensor] = None,
-                out64: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """(d) of north_star / demux.py:113-118 -> genotype_addition float32 [V, G] (+ all-reduce when sharded)."""
+                buffers: Optional[dict] = None) -> torch.Tensor:
+        """(d) of north_star / demux.py:113-118 -> genotype_addition float32 [V, G] (+ cross-GPU sum when sharded).
+        `out`: a [v_pad, G] table of _mstep_buffers (sharded) or any [V, G] float32 tensor (single GPU)."""
         lib = _native.load()
         dev = pack.device
         sharded = cls.process_group is not None
-        if out is None:
-            out = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float32, device=dev)
-        wide = sharded and cls.mstep_allreduce_dtype == 'float64'
-        if wide and out64 is None:
-            out64 = torch.empty((pack.n_variants, pack.n_genotypes), dtype=torch.float64, device=dev)
+        V, G = pack.n_variants, pack.n_genotypes
         with torch.cuda.device(dev):
             plan = cls._mstep_plan(pack)
-
-            def launch(v_lo: int, v_hi: int) -> None:
+            blob, n_medium, n_heavy_variants, n_heavy_items, scratch = plan if plan is not None else (None, 0, 0, 0, None)
+            if not sharded:
+                if out is None:
+                    out = torch.empty((V, G), dtype=torch.float32, device=dev)
                 common = (pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
-                          singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, float(cls.contribution_power),
-                          0 if wide else out.data_ptr(), pack.n_genotypes, _native.ptr(out64) if wide else 0,
-                          pack.n_genotypes, v_lo, v_hi)
+                          singlets.data_ptr(), singlets.shape[1], G, float(cls.contribution_power),
+                          out.data_ptr(), G, 0, G, 0, V)
                 if plan is None:
                     _native.check(lib.dmx_mstep(*common, _stream()), 'dmx_mstep')
                 else:
-                    blob, n_medium, n_heavy_variants, n_heavy_items, scratch = plan
                     _native.check(lib.dmx_mstep_planned(*common, blob.data_ptr(), pack.n_rows, n_medium,
                                                         n_heavy_variants, n_heavy_items, scratch.data_ptr(),
                                                         _stream()), 'dmx_mstep_planned')
-
-            if not sharded:
-                launch(0, pack.n_variants)
-                return out
-            # (f) of north_star: the partial variant x genotype sums of all barcode shards are combined with one
-            # sum all-reduce per EM iteration.  The variant range is cut into tiles: NCCL reduces tile k (on its
-            # own stream, async_op) while the M-step kernel computes tile k + 1.  Partials travel as float64 so
-            # the single rounding to float32 happens after the global sum, exactly as on one GPU
-            # (mstep_allreduce_dtype = 'float32' halves the bytes on the wire at the price of one extra float32
-            # rounding per shard: about world_size ulp on the addition, far inside the parity tolerance).
+                return out[:V]
+            # (f) of north_star: the partial variant x genotype sums of all barcode shards are combined once per EM
+            # iteration: dmx_mstep_allreduce computes the M-step over tiles of the variant range and NCCL sums tile k
+            # (on the communicator's stream) while the kernel computes tile k + 1.
+            from .distributed import native_comm
+            if buffers is None:
+                buffers = cls._mstep_buffers(pack)
+            if out is None:
+                out = buffers['tables'][0]
+            wide = cls.mstep_allreduce_dtype == 'float64'
+            comm = native_comm(cls.process_group, dev)
+            if comm is not None:
+                _native.check(lib.dmx_mstep_allreduce(
+                    pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(), singlets.data_ptr(),
+                    singlets.shape[1], G, float(cls.contribution_power), out.data_ptr(),
+                    _native.ptr(buffers.get('partial64')) if wide else 0,
+                    _native.ptr(buffers.get('slice64')) if wide else 0, V, _native.ptr(blob), pack.n_rows, n_medium,
+                    n_heavy_variants, n_heavy_items, _native.ptr(scratch), comm, int(cls.mstep_allreduce_tiles),
+                    1 if wide else 0, _stream()), 'dmx_mstep_allreduce')
+                return out[:V]
+            # process groups without NCCL (gloo over CUDA tensors): same algebra through torch.distributed
             import torch.distributed as dist
-            partial = out64 if wide else out
-            n_tiles = max(1, min(cls.mstep_allreduce_tiles, pack.n_variants))
-            bounds = [pack.n_variants * k // n_tiles for k in range(n_tiles + 1)]
-            pending = []
-            for v_lo, v_hi in zip(bounds[:-1], bounds[1:]):
-                if v_hi > v_lo:
-                    launch(v_lo, v_hi)
-                    pending.append(dist.all_reduce(partial[v_lo:v_hi], op=dist.ReduceOp.SUM,
-                                                   group=cls.process_group, async_op=True))
-            for work in pending:
-                work.wait()
-            if not wide:
-                return out
-            _native.check(lib.dmx_round_f64_to_f32(
-                out64.data_ptr(), pack.n_genotypes, out.data_ptr(), pack.n_genotypes, pack.n_variants,
-                pack.n_genotypes, _stream()), 'dmx_round_f64_to_f32')
-        return out
+            partial = buffers['partial64'] if wide else out
+            common = (pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
+                      singlets.data_ptr(), singlets.shape[1], G, float(cls.contribution_power),
+                      0 if wide else out.data_ptr(), G, partial.data_ptr() if wide else 0, G, 0, V)
+            if plan is None:
+                _native.check(lib.dmx_mstep(*common, _stream()), 'dmx_mstep')
+            else:
+                _native.check(lib.dmx_mstep_planned(*common, blob.data_ptr(), pack.n_rows, n_medium, n_heavy_variants,
+                                                    n_heavy_items, scratch.data_ptr(), _stream()), 'dmx_mstep_planned')
+            dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=cls.process_group)
+            if wide:
+                _native.check(lib.dmx_round_f64_to_f32(partial.data_ptr(), G, out.data_ptr(), G, V, G, _stream()),
+                              'dmx_round_f64_to_f32')
+        return out[:V]
 
     # ------------------------------------------------------------------------------------------------ aggregate_on_snps
     @classmethod
@@ -611,7 +796,7 @@ class Demultiplexer:
                 _native.check(-1, 'dmx_snp_groups_workspace_bytes')
             workspace = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
             h_matched, h_groups = C.c_int64(0), C.c_int64(0)
-            lo, hi = pack.barcode_range
+            lo, hi = 0, pack.n_barcodes  # barcode ids of a pack are local to its range
             with torch.cuda.device(dev):
                 variant2snp = _to_device(np.ascontiguousarray(pack.variant2snp, dtype=np.int32), dev)
                 _native.check(lib.dmx_build_snp_groups(
@@ -681,7 +866,7 @@ class Demultiplexer:
                            p_genotype_clip=0.01, doublet_prior=0.35):
         """One E-step with the given genotypes (demux.py:120-156): returns (logits_df, probs_df)."""
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
-                                add_data_prior=False)
+                                add_data_prior=False, keep_calls=cls.aggregate_on_snps)
         table = cls._probs_table(pack, None, p_genotype_clip)
         table_is_finite = torch.isfinite(table).all()  # demux.py:135; read back together with the results
         logits, post, _ = cls._e_step_any(pack, table, doublet_prior)
@@ -719,7 +904,7 @@ class Demultiplexer:
         if barcode_prior_logits is not None:
             assert barcode_prior_logits.shape == (barcode_handler.n_barcodes, n_cols), 'wrong shape of priors'
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
-                                add_data_prior=True)
+                                add_data_prior=True, keep_calls=cls.aggregate_on_snps)
         pack.check()
         prior_dev = cls._prior_logits_to_device(barcode_prior_logits, barcode_handler.n_barcodes, n_cols, pack.device)
         names = option_names(genotypes.genotype_names, doublet_prior)
@@ -757,7 +942,7 @@ class Demultiplexer:
         if barcode_prior_logits is not None:
             assert barcode_prior_logits.shape == (barcode_handler.n_barcodes, n_cols), 'wrong shape of priors'
         pack = cls._pack_device(chromosome2compressed_snp_calls, genotypes, barcode_handler.n_barcodes,
-                                add_data_prior=True)
+                                add_data_prior=True, keep_calls=cls.aggregate_on_snps)
         pack.check()
         prior_dev = cls._prior_logits_to_device(barcode_prior_logits, barcode_handler.n_barcodes, n_cols, pack.device)
         post, addition = cls._em_iterations(pack, n_iterations, p_genotype_clip, doublet_prior, prior_dev)
@@ -768,25 +953,24 @@ class Demultiplexer:
 
     @classmethod
     def _em_iterations(cls, pack: DevicePack, n_iterations: int, p_genotype_clip: float, doublet_prior: float,
-                       prior_logits: Optional[torch.Tensor]):
+                       prior_logits: Optional[torch.Tensor], want_post: bool = True):
         """Device-resident EM loop; returns (posteriors [B, C] of the last E-step, addition that fed it)."""
         buffers: dict = {}
-        addition = torch.zeros_like(pack.betas)
-        spare = torch.empty_like(pack.betas)
-        spare64 = torch.empty(pack.betas.shape, dtype=torch.float64, device=pack.device) \
-            if cls.process_group is not None else None
+        mbuf = cls._mstep_buffers(pack)
+        V = pack.n_variants
+        addition, spare = mbuf['tables']
         table = None
         post = None
         for iteration in range(n_iterations):
             last = iteration == n_iterations - 1
-            table = cls._probs_table(pack, addition, p_genotype_clip, out=table)
+            table = cls._probs_table(pack, addition[:V], p_genotype_clip, out=table)
             _, post, singlets = cls._e_step_any(
                 pack, table, doublet_prior, prior_logits=prior_logits if iteration == 0 else None,
-                want_logits=False, want_post=last, want_singlets=not last, buffers=buffers)
+                want_logits=False, want_post=last and want_post, want_singlets=not last, buffers=buffers)
             if not last:
-                new_addition = cls._m_step(pack, singlets, out=spare, out64=spare64)
-                spare, addition = addition, new_addition
-        return post, addition
+                cls._m_step(pack, singlets, out=spare, buffers=mbuf)
+                spare, addition = addition, spare
+        return post, addition[:V]
 
 
 def _as_dtype(array: np.ndarray, dtype: np.dtype) -> np.ndarray:

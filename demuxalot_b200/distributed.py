@@ -3,15 +3,18 @@ Multi-GPU EM: one process per GPU (torch.distributed, NCCL over NVLink), work pa
 
 The E-step is barcode-local (a barcode's rows and the replicated probability table are all it reads), so it
 needs no communication.  The M-step on a barcode shard yields a partial variant x genotype sum; the partials are
-combined with ONE all-reduce per EM iteration, pipelined against the M-step kernel over
-tiles of the variant range (`Demultiplexer._m_step`).  Partials travel as float64 and are rounded to float32 once
-after the global sum, exactly where the single-GPU path rounds.  The only other exchange is a one-off integer
+combined ONCE per EM iteration by `dmx_mstep_allreduce` (csrc/comm.cu): the M-step kernel
+runs over tiles of the variant range and NCCL sums tile k while the kernel computes tile k + 1.  Partials travel as
+float64 (reduce-scatter), are rounded to float32 once after the global sum, exactly where the single-GPU path
+rounds, and the float32 slices are all-gathered.  The only other exchange is a one-off integer
 all-reduce of the per-variant molecule counts that enter the data prior (demux.py:381).
 
 Two ways to use it (both need `torch.distributed` initialised, one rank per GPU):
 
-  * sharded(): every rank is given the SAME full inputs; rank r keeps the calls of its contiguous barcode range
-    (balanced by call count) and returns the posteriors of that range, optionally gathered to all ranks;
+  * learn_genotypes_sharded(): every rank is given the SAME full inputs; rank r uploads and matches the r-th slice
+    of the calls, the matched calls are exchanged over NVLink (one all-to-all) so that each rank sorts and keeps one
+    contiguous barcode range (balanced by matched calls), and the posteriors of that range are returned, optionally
+    gathered to all ranks;
   * lanes: every rank is given ITS OWN calls / barcode handler (e.g. one 10x lane per GPU sharing the donors);
     wrap the usual `Demultiplexer.learn_genotypes` call in `with em_group(group):`.
 """
@@ -68,13 +71,82 @@ def em_group(group=None):
         Demultiplexer.process_group = previous
 
 
+def exchange_calls(send, counts: List[int], n_bad: int, group, device):
+    """
+    All-to-all of the routed calls (sharded pack).  `send`: tensors whose first sum(counts) entries are grouped by
+    destination rank (counts[d] entries for rank d).  Returns (received tensors, n_received, total n_bad): blocks
+    arrive in source-rank order and ranks hold consecutive slices of every chromosome's calls, so call order is kept
+    inside every chromosome -- hence inside every (variant, barcode) group, which is all demux.py:282-283 needs.  Backend-agnostic (NCCL on the GPUs, gloo in the CPU tests).
+    """
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    meta = torch.tensor(list(counts) + [n_bad], dtype=torch.int64, device=device)
+    gathered = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(gathered, meta, group=group)
+    table = torch.stack(gathered).cpu()
+    total_bad = int(table[:, world].sum())
+    recv_counts = [int(table[src, rank]) for src in range(world)]
+    n_recv, n_send = sum(recv_counts), sum(counts)
+    received = []
+    for t in send:
+        r = torch.empty(max(n_recv, 1), dtype=t.dtype, device=device)
+        if total_bad == 0:
+            dist.all_to_all_single(r[:n_recv], t[:n_send], recv_counts, list(counts), group=group)
+        received.append(r)
+    return received, n_recv, total_bad
+
+
+_NATIVE_COMMS: dict = {}
+
+
+def native_comm(group, device):
+    """The library's own NCCL communicator for `group` (dmx_comm_init), created on first use; None when the group
+    does not run on NCCL (then `Demultiplexer._m_step` goes through torch.distributed)."""
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    from . import _native
+    if dist.get_backend(group) != 'nccl':
+        return None
+    key = (id(group), torch.device(device).index)
+    if key not in _NATIVE_COMMS:
+        lib = _native.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        unique_id = (C.c_uint8 * 128)()
+        if rank == 0:
+            _native.check(lib.dmx_comm_unique_id(unique_id), 'dmx_comm_unique_id')
+        box = [bytes(unique_id)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0), group=group)
+        unique_id = (C.c_uint8 * 128).from_buffer_copy(box[0])
+        handle = C.c_void_p()
+        with torch.cuda.device(device):
+            _native.check(lib.dmx_comm_init(unique_id, rank, world, C.byref(handle)), 'dmx_comm_init')
+        _NATIVE_COMMS[key] = handle
+    return _NATIVE_COMMS[key]
+
+
+def release_native_comms() -> None:
+    from . import _native
+    lib = _native.load()
+    for handle in _NATIVE_COMMS.values():
+        lib.dmx_comm_destroy(handle)
+    _NATIVE_COMMS.clear()
+
+
 def learn_genotypes_sharded(chromosome2compressed_snp_calls, genotypes, barcode_handler, n_iterations=5,
                             p_genotype_clip=0.01, doublet_prior=0., barcode_prior_logits: np.ndarray = None,
-                            group=None, gather_posteriors: bool = True):
+                            group=None, gather_posteriors: bool = True, device_parts=None):
     """
     Barcode-sharded `learn_genotypes`: same arguments on every rank, same learnt genotypes on every rank.
+    Rank r uploads and matches the r-th slice of every chromosome's calls; the matched calls are exchanged so that
+    each rank sorts and keeps one contiguous barcode range (balanced by matched calls); per EM iteration the M-step
+    partials are summed across the ranks (`Demultiplexer._m_step`).
     Returns (learnt genotypes, posteriors DataFrame).  With gather_posteriors the frame covers all barcodes on
     every rank; otherwise only the rows of this rank's barcode range.
+    `device_parts`: this rank's share of the calls already on its GPU (see Demultiplexer._unpack_device_parts)
+    instead of `chromosome2compressed_snp_calls`.
     """
     import pandas as pd
     import torch
@@ -90,31 +162,25 @@ def learn_genotypes_sharded(chromosome2compressed_snp_calls, genotypes, barcode_
     if barcode_prior_logits is not None:
         assert barcode_prior_logits.shape == (n_barcodes, n_cols), 'wrong shape of priors'
 
-    shards = plan_barcode_shards(calls_per_barcode(chromosome2compressed_snp_calls, n_barcodes), world)
-    lo, hi = shards[rank]
     with em_group(group):
-        # every rank sees every call, so the molecule counts of the data prior are already global: no all-reduce
-        saved, Demultiplexer.process_group = Demultiplexer.process_group, None
-        try:
-            pack = Demultiplexer._pack_device(chromosome2compressed_snp_calls, genotypes, n_barcodes,
-                                              add_data_prior=True, barcode_range=(lo, hi))
-        finally:
-            Demultiplexer.process_group = saved
+        pack = Demultiplexer._pack_device(chromosome2compressed_snp_calls, genotypes, n_barcodes, add_data_prior=True,
+                                          shard=(rank, world, group), device_parts=device_parts, keep_calls=False)
         pack.check()
-        prior_dev = Demultiplexer._prior_logits_to_device(barcode_prior_logits, n_barcodes, n_cols, pack.device)
+        lo, hi = pack.barcode_range
+        prior_dev = Demultiplexer._prior_logits_to_device(
+            None if barcode_prior_logits is None else barcode_prior_logits[lo:hi], hi - lo, n_cols, pack.device)
         post, addition = Demultiplexer._em_iterations(pack, n_iterations, p_genotype_clip, doublet_prior, prior_dev)
     names = option_names(genotypes.genotype_names, doublet_prior)
     learnt = genotypes._with_betas((pack.raw_betas + addition).cpu().numpy())
     if gather_posteriors:
-        # barcodes outside a rank's range have no rows there; every rank contributes its own block
-        counts = [h - l for l, h in shards]
-        blocks = [torch.empty((c, n_cols), dtype=torch.float32, device=pack.device) for c in counts]
-        mine = post[lo:hi].contiguous()
-        dist.all_gather(blocks, mine, group=group) if len(set(counts)) == 1 else _all_gather_ragged(blocks, mine, group)
+        # every rank contributes the block of its own barcode range
+        ranges = [None] * world
+        dist.all_gather_object(ranges, (lo, hi), group=group)
+        blocks = [torch.empty((h - l, n_cols), dtype=torch.float32, device=pack.device) for l, h in ranges]
+        _all_gather_ragged(blocks, post.contiguous(), group)
         full = torch.cat(blocks, dim=0).cpu().numpy()
         return learnt, pd.DataFrame(data=full, index=barcode_handler.ordered_barcodes, columns=names)
-    return learnt, pd.DataFrame(data=post[lo:hi].cpu().numpy(), index=barcode_handler.ordered_barcodes[lo:hi],
-                                columns=names)
+    return learnt, pd.DataFrame(data=post.cpu().numpy(), index=barcode_handler.ordered_barcodes[lo:hi], columns=names)
 
 
 def _all_gather_ragged(blocks, mine, group) -> None:

@@ -20,7 +20,7 @@ import pandas as pd
 from .bam import BamFile
 from .barcodes import BarcodeHandler
 from .calls import CompressedSNPCalls
-from .counting import _open_cached, count_coverage_native, count_snps, parse_read as cellranger_parse_read
+from .counting import _bam_info, _open_cached, count_coverage_native, count_snps, parse_read as cellranger_parse_read
 from .genotype_store import ProbabilisticGenotypes
 
 _BASE_CODE = np.full(256, -1, dtype=np.int8)
@@ -197,8 +197,8 @@ def detect_snps_positions(bamfile_location, genotypes: ProbabilisticGenotypes, b
 
     # step 2: collect SNPs using the predictions of the rough demultiplexing
     filename = bamfile_location if isinstance(bamfile_location, (str, Path)) else list(bamfile_location.values())[0]
-    bam = _open_cached(filename)
-    chromosomes = list(zip(bam.references, bam.lengths))
+    info = _bam_info(filename)  # header only: the alignments are streamed by the counting tasks, never held whole
+    chromosomes = list(zip(info['names'], info['lengths']))
     sorted_donors = np.unique([donor for donor in barcode2donor.values()])
     tasks = [dict(bamfile_path=bamfile_location, chromosome=chromosome, start=start,
                   stop=min(start + max_fragment_step, length), barcode2donor=barcode2donor, parse_read=parse_read,

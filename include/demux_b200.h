@@ -26,11 +26,13 @@
 extern "C" {
 #endif
 
-#define DMX_ABI_VERSION 3
+#define DMX_ABI_VERSION 4
 
 /* E-step arithmetic flavours (see DESIGN.md "E-step") */
 #define DMX_ESTEP_EXACT 0 /* per-term float32 argument roundings + logf of demux.py:261, float64 accumulation */
-#define DMX_ESTEP_FAST 1  /* a = fma(P, 1-e, e'), products of 8 row factors, one lg2 per product, float64 accumulation */
+#define DMX_ESTEP_FAST 1  /* a = fma(P, 1-e, e'), products of 8 or 16 row factors, one lg2 per product, float64 accumulation */
+#define DMX_ESTEP_AUTO 2  /* EXACT where the E-step is bound by the row stream (singlet columns only, or <= 8 genotypes),
+                             FAST for the FP32-bound pair kernels (doublet columns, more than 8 genotypes) */
 
 /* ---- boundary smoke ------------------------------------------------------------------------------- */
 int dmx_abi_version(void);
@@ -215,6 +217,51 @@ int dmx_snp_logits(const int64_t* barcode_group_offsets, const int64_t* group_of
 int dmx_softmax_rows_f64(double* logits, int64_t ld_logits, const double* prior_logits, int64_t ld_prior, int64_t n_rows,
                          int32_t n_cols, double* posteriors, int64_t ld_post, float* singlet_posteriors,
                          int64_t ld_singlet, int32_t n_singlets, void* stream);
+
+/* ---- sharded pack (multi-GPU) --------------------------------------------------------------
+ * The reference packs on one host (demux.py:302-392; its only split is the per-chromosome loop at :334-358).  Across
+ * GPUs every rank uploads and unpacks a contiguous SLICE of each chromosome's calls; the matched calls then move to
+ * the rank that owns their barcode (contiguous barcode ranges balanced by matched calls), so that a rank sorts and
+ * keeps only its shard.  The exchange itself is an all-to-all the host issues (torch.distributed / NCCL).
+ *
+ * dmx_barcode_histogram: histogram[b] += matched calls of barcode b (int64 [n_barcodes], accumulated: zero it first).
+ * dmx_route_calls: stable partition of the matched calls by owner rank; cuts (device, int64 [world + 1]) are the
+ * barcode range boundaries, cuts[0] = 0, cuts[world] = n_barcodes.  Outputs (capacity n_calls): the kept calls grouped
+ * by destination rank, original order inside a group, with out_cb LOCAL to the owner's range (cb - cuts[dest]).
+ * h_counts (host, int64 [world + 1]): calls per destination; the last entry counts matched calls whose compressed_cb
+ * lies outside [0, n_barcodes) (an input error the caller must raise on every rank).  Synchronises `stream`.
+ */
+int dmx_barcode_histogram(const int32_t* call_variant, const int32_t* call_cb, int64_t n_calls, int64_t n_variants,
+                          int64_t n_barcodes, int64_t* histogram, void* stream);
+int64_t dmx_route_calls_workspace_bytes(int64_t n_calls);
+int dmx_route_calls(const int32_t* call_variant, const int32_t* call_cb, const float* call_e, int64_t n_calls,
+                    int64_t n_variants, int64_t n_barcodes, const int64_t* cuts, int32_t world, void* workspace,
+                    int64_t workspace_bytes, int32_t* out_variant, int32_t* out_cb, float* out_e, int64_t* h_counts,
+                    void* stream);
+
+/* ---- (f) M-step + cross-GPU sum: demux.py:113-118 on barcode shards ---------------------------------------------------
+ * One communicator per process (one process per GPU).  dmx_comm_unique_id (rank 0; h_id128 = 128 host bytes, to be
+ * broadcast by the host's own means) and dmx_comm_init wrap ncclGetUniqueId / ncclCommInitRank; NCCL is bound with
+ * dlopen at the first call, there is no link-time dependency.
+ *
+ * dmx_mstep_allreduce = dmx_mstep[_planned] over n_tiles tiles of the variant range, each finished tile handed to NCCL
+ * on the communicator's own stream while the kernel of the next tile runs; `stream` waits for the last collective
+ * before the call's successors run.  On return (stream order) `addition` holds the float32 GLOBAL sums on every rank.
+ *   wire_float64 != 0: reduce-scatter of float64 partials (partial64 [v_pad, G]), this rank's slice rounded to
+ *     float32 once (slice64: float64 scratch of ceil(v_pad / n_tiles + world) * G / world elements), all-gather of
+ *     the float32 slices;  wire_float64 == 0: in-place float32 all-reduce (partial64 / slice64 may be NULL).
+ * `addition` (and partial64) must hold v_pad = dmx_mstep_allreduce_padded_variants(n_variants, world) rows of G
+ * contiguous floats, rows [n_variants, v_pad) zeroed by the caller once.  plan == NULL: unplanned M-step.
+ */
+int dmx_comm_unique_id(uint8_t* h_id128);
+int dmx_comm_init(const uint8_t* h_id128, int32_t rank, int32_t world, void** h_comm);
+int dmx_comm_destroy(void* comm);
+int64_t dmx_mstep_allreduce_padded_variants(int64_t n_variants, int32_t world);
+int dmx_mstep_allreduce(const int64_t* variant_offsets, const int32_t* csc_cb, const float* csc_e,
+                        const float* singlet_posteriors, int64_t ld_singlet, int32_t n_genotypes, double power,
+                        float* addition, double* partial64, double* slice64, int64_t n_variants, const void* plan,
+                        int64_t n_rows, int64_t n_medium, int64_t n_heavy_variants, int64_t n_heavy_items,
+                        double* heavy_scratch, void* comm, int32_t n_tiles, int32_t wire_float64, void* stream);
 
 /* float32(out) = float32(in64) elementwise over a [rows, cols] matrix (after an all-reduce of float64 partials) */
 int dmx_round_f64_to_f32(const double* in64, int64_t ld_in, float* out, int64_t ld_out, int64_t n_rows,

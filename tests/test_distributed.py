@@ -97,6 +97,79 @@ def test_barcode_sharding_algebra_gloo_world2(tmp_path):
     assert np.array_equal(c0, np.load(tmp_path / 'lane_0.npy') + np.load(tmp_path / 'lane_1.npy'))
 
 
+
+def _route_numpy(variant, cb, e, cuts):
+    """numpy statement of dmx_route_calls: matched calls grouped by owner rank, stable, barcode ids local."""
+    keep = variant >= 0
+    dest = np.searchsorted(np.asarray(cuts[1:-1]), cb, side='right')
+    order = np.flatnonzero(keep)[np.argsort(dest[keep], kind='stable')]
+    counts = np.bincount(dest[keep], minlength=len(cuts) - 1)
+    return variant[order], cb[order] - np.asarray(cuts)[dest[order]], e[order], counts
+
+
+def _exchange_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from demuxalot_b200.distributed import exchange_calls, plan_barcode_shards
+    from demuxalot_b200.synthetic import make_dataset
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        ds = make_dataset(n_genotypes=5, n_snps=200, n_barcodes=40, rows_per_barcode=60, seed=77)
+        B = 40
+        v2s = oracle.snp_ids_for_variants(ds.genotypes.var2varid)
+        # every call in dict / call order with its variant (-1: unmatched), as dmx_unpack_match_calls leaves them
+        variant, cb, e = [], [], []
+        keys = {k: v for k, v in ds.genotypes.var2varid.items()}
+        for chrom, c in ds.calls.items():
+            sc, mols = c.snp_calls[:c.n_snp_calls], c.molecules[:c.n_molecules]
+            lo, hi = c.n_snp_calls * rank // world, c.n_snp_calls * (rank + 1) // world  # this rank's slice
+            for rec in sc[lo:hi]:
+                variant.append(keys.get((chrom, int(rec['snp_position']), 'ACGTN'[rec['base_index']]), -1))
+                cb.append(int(mols['compressed_cb'][rec['molecule_index']]))
+                e.append(rec['p_base_wrong'])
+        variant, cb, e = np.array(variant, np.int32), np.array(cb, np.int32), np.array(e, np.float32)
+        hist = torch.from_numpy(np.bincount(cb[variant >= 0], minlength=B).astype(np.int64))
+        dist.all_reduce(hist)
+        ranges = plan_barcode_shards(hist.numpy(), world)
+        cuts = [r[0] for r in ranges] + [B]
+        sv, scb, se, counts = _route_numpy(variant, cb, e, cuts)
+        received, n, bad = exchange_calls([torch.from_numpy(x.copy()) for x in (sv, scb, se)],
+                                          [int(c) for c in counts], 0, dist.group.WORLD, 'cpu')
+        assert bad == 0
+        np.savez(os.path.join(out_dir, f'shard_{rank}.npz'), variant=received[0][:n].numpy(), cb=received[1][:n].numpy(),
+                 e=received[2][:n].numpy(), lo=ranges[rank][0], hi=ranges[rank][1])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_pack_exchange_keeps_call_order_gloo_world2(tmp_path):
+    """Slices of the calls -> route by barcode range -> all-to-all: every rank ends up with exactly the matched calls of
+    its barcode range, call order kept inside every variant (what the ordered float32 products of demux.py:282-283
+    need)."""
+    import torch.multiprocessing as mp
+    import oracle
+    from demuxalot_b200.synthetic import make_dataset
+    mp.spawn(_exchange_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    ds = make_dataset(n_genotypes=5, n_snps=200, n_barcodes=40, rows_per_barcode=60, seed=77)
+    v2s = oracle.snp_ids_for_variants(ds.genotypes.var2varid)
+    flat = oracle.match_and_flatten_calls(ds.calls, ds.genotypes.var2varid, v2s)
+    mv, mcb, me = flat['variant_id'], flat['compressed_cb'], flat['p_base_wrong']
+    covered = 0
+    for rank in range(2):
+        got = np.load(tmp_path / f'shard_{rank}.npz')
+        lo, hi = int(got['lo']), int(got['hi'])
+        mine = (mcb >= lo) & (mcb < hi)
+        # call order is kept inside every chromosome (slices of different chromosomes interleave by rank), hence
+        # inside every variant and every (variant, barcode) group: compare after a stable sort by variant
+        a, b = np.argsort(got['variant'], kind='stable'), np.argsort(mv[mine], kind='stable')
+        assert np.array_equal(got['variant'][a], mv[mine][b])
+        assert np.array_equal(got['cb'][a], (mcb[mine] - lo)[b])
+        assert np.array_equal(got['e'][a].view(np.uint32), me[mine][b].view(np.uint32))
+        covered += int(mine.sum())
+    assert covered == len(mv)
+
 def test_em_group_requires_initialised_process_group():
     from demuxalot_b200.distributed import em_group
     with pytest.raises(AssertionError):
@@ -131,15 +204,24 @@ def _nccl_worker(rank: int, world: int, port: int, out_dir: str) -> None:
             lane_learnt, _ = Demultiplexer.learn_genotypes(lane.calls, lane.genotypes, lane.barcode_handler,
                                                            n_iterations=3, doublet_prior=0.35)
         np.save(os.path.join(out_dir, f'lane_betas_{rank}.npy'), np.array(lane_learnt.get_betas()))
+        # the sharded pack itself: this rank's rows = the oracle's rows of its barcode range, local barcode ids
+        with em_group():
+            pack = Demultiplexer._pack_device(ds.calls, ds.genotypes, 200, add_data_prior=True,
+                                              shard=(rank, world, dist.group.WORLD))
+        np.savez(os.path.join(out_dir, f'pack_{rank}.npz'), variant=pack.csc_variant.cpu().numpy(),
+                 cb=pack.csc_cb.cpu().numpy(), e=pack.csc_e.cpu().numpy(), n_mol=pack.n_mol.cpu().numpy(),
+                 betas=pack.betas.cpu().numpy(), lo=pack.barcode_range[0], hi=pack.barcode_range[1])
         # float32 partial sums on the wire: one extra rounding per shard, otherwise the same protocol
         Demultiplexer.mstep_allreduce_dtype, Demultiplexer.mstep_allreduce_tiles = 'float32', 3
         try:
             narrow, _ = learn_genotypes_sharded(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4,
                                                 doublet_prior=0.35)
         finally:
-            Demultiplexer.mstep_allreduce_dtype, Demultiplexer.mstep_allreduce_tiles = 'float64', 1
+            Demultiplexer.mstep_allreduce_dtype, Demultiplexer.mstep_allreduce_tiles = 'float64', 2
         np.save(os.path.join(out_dir, f'betas_f32_{rank}.npy'), np.array(narrow.get_betas()))
     finally:
+        from demuxalot_b200.distributed import release_native_comms
+        release_native_comms()
         dist.destroy_process_group()
 
 
@@ -158,3 +240,48 @@ def test_two_gpu_sharded_em_matches_single_gpu(tmp_path, native_lib):
     assert np.array_equal(np.load(tmp_path / 'lane_betas_0.npy'), np.load(tmp_path / 'lane_betas_1.npy'))
     n0, n1 = np.load(tmp_path / 'betas_f32_0.npy'), np.load(tmp_path / 'betas_f32_1.npy')
     assert np.array_equal(n0, n1) and np.allclose(n0, bs, rtol=2e-6, atol=1e-7)
+    # against the oracle: learnt betas, the shards' rows and the data prior
+    import oracle
+    from demuxalot_b200.synthetic import make_dataset
+    ds = make_dataset(n_genotypes=12, n_snps=1500, n_barcodes=200, rows_per_barcode=150, seed=41)
+    O = oracle.OracleDemultiplexer
+    want, _ = O.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4, doublet_prior=0.35)
+    wb = np.array(want.get_betas(), np.float64)
+    assert (np.abs(b0 - wb) / np.maximum(np.abs(wb), 1e-3)).max() <= 1e-5
+    _, obetas, omol, orows = O.pack_calls(ds.calls, ds.genotypes, True)
+    n_rows = 0
+    for rank in range(2):
+        got = np.load(tmp_path / f'pack_{rank}.npz')
+        lo, hi = int(got['lo']), int(got['hi'])
+        mine = (orows['compressed_cb'] >= lo) & (orows['compressed_cb'] < hi)
+        assert np.array_equal(got['variant'], orows['variant_id'][mine])
+        assert np.array_equal(got['cb'], orows['compressed_cb'][mine] - lo)
+        assert np.array_equal(got['e'].view(np.uint32), orows['p_base_wrong'][mine].view(np.uint32))
+        assert np.array_equal(got['n_mol'], np.bincount(omol['variant_id'], minlength=len(obetas)))  # summed over ranks
+        assert np.array_equal(got['betas'].view(np.uint32), obetas.view(np.uint32))
+        n_rows += int(mine.sum())
+    assert n_rows == len(orows['variant_id'])
+    # lanes: the reference's equivalent is one run over the union of the lanes (BarcodeHandler over all of them)
+    from demuxalot_b200 import CompressedSNPCalls
+    lanes = [make_dataset(n_genotypes=12, n_snps=1500, n_barcodes=100, rows_per_barcode=150, seed=41, calls_seed=r)
+             for r in range(2)]
+    union = {}
+    for chrom in lanes[0].calls:
+        parts = []
+        for k, lane in enumerate(lanes):
+            c = lane.calls[chrom]
+            shifted = CompressedSNPCalls.__new__(CompressedSNPCalls)
+            shifted.molecules = c.molecules[:c.n_molecules].copy()
+            shifted.molecules['compressed_cb'] += 100 * k
+            shifted.snp_calls, shifted.n_molecules, shifted.n_snp_calls = c.snp_calls[:c.n_snp_calls].copy(), c.n_molecules, c.n_snp_calls
+            parts.append(shifted)
+        union[chrom] = CompressedSNPCalls.concatenate(parts)
+
+    class UnionHandler:
+        n_barcodes = 200
+        ordered_barcodes = [str(k) for k in range(200)]
+
+    want_lanes, _ = O.learn_genotypes(union, lanes[0].genotypes, UnionHandler, n_iterations=3, doublet_prior=0.35)
+    wl = np.array(want_lanes.get_betas(), np.float64)
+    lb = np.load(tmp_path / 'lane_betas_0.npy')
+    assert (np.abs(lb - wl) / np.maximum(np.abs(wl), 1e-3)).max() <= 1e-5

@@ -83,11 +83,12 @@ def test_shards_and_mstep_additivity_at_full_size(full):
     lib = _native.load()
     for lo, hi in ((0, B // 2), (B // 2, B)):
         shard = D._pack_device(ds.calls, ds.genotypes, B, add_data_prior=True, barcode_range=(lo, hi))
+        assert shard.n_barcodes == hi - lo and shard.barcode_range == (lo, hi)  # barcode ids local to the range
         shard_logits, _, _ = D._e_step(shard, table, 0.35, want_post=False)
-        assert torch.equal(shard_logits[lo:hi], logits[lo:hi])  # the E-step is barcode-local: bit-identical
+        assert torch.equal(shard_logits, logits[lo:hi])  # the E-step is barcode-local: bit-identical
         part64 = torch.empty_like(total64)
         assert lib.dmx_mstep(shard.variant_offsets.data_ptr(), shard.csc_cb.data_ptr(), shard.csc_e.data_ptr(),
-                             singlets.data_ptr(), singlets.shape[1], pack.n_genotypes, 2.0, 0, 0, part64.data_ptr(),
+                             singlets[lo:hi].data_ptr(), singlets.shape[1], pack.n_genotypes, 2.0, 0, 0, part64.data_ptr(),
                              pack.n_genotypes, 0, pack.n_variants, torch.cuda.current_stream().cuda_stream) == 0
         total64 += part64
         del shard

@@ -30,7 +30,7 @@ from golden_io import CASES, bits, load_case
 
 pytestmark = pytest.mark.gpu
 
-FLAVOURS = ['fast', 'exact']
+FLAVOURS = ['auto', 'fast', 'exact']
 REPORT = {}
 
 
@@ -40,13 +40,19 @@ def D(native_lib):
     assert torch.cuda.is_available(), 'GPU tests need a CUDA device'
     from demuxalot_b200 import Demultiplexer
     yield Demultiplexer
-    Demultiplexer.estep_flavour = 'fast'
+    Demultiplexer.estep_flavour = 'auto'
     out = Path(os.environ.get('GRAFT_REPO_ROOT', Path(__file__).resolve().parent.parent)) / 'gpurun_out'
     out.mkdir(exist_ok=True)
     (out / 'parity_report.json').write_text(json.dumps(REPORT, indent=1, sort_keys=True))
 
 
-def check_logits_and_posteriors(tag, got_logits, want_logits, got_post, want_post):
+def reference_rounding(flavour: str, n_genotypes: int, doublet_prior: float) -> bool:
+    """True when the E-step runs on the reference's own per-term roundings (DMX_ESTEP_EXACT, or DMX_ESTEP_AUTO on the
+    row-stream-bound paths: singlet columns only, or at most 8 genotypes): there the posterior bar is a flat 1e-6."""
+    return flavour == 'exact' or (flavour == 'auto' and (doublet_prior == 0 or n_genotypes <= 8))
+
+
+def check_logits_and_posteriors(tag, got_logits, want_logits, got_post, want_post, flat=False):
     got_logits, want_logits = np.asarray(got_logits, np.float64), np.asarray(want_logits, np.float64)
     rel = np.abs(got_logits - want_logits) / np.maximum(np.abs(want_logits), 1e-30)
     rel[want_logits == 0] = np.abs(got_logits - want_logits)[want_logits == 0]
@@ -61,6 +67,8 @@ def check_logits_and_posteriors(tag, got_logits, want_logits, got_post, want_pos
     assert rel.max(initial=0) <= 1e-5, f'{tag}: logits differ by {rel.max()} relative'
     bound = 1e-6 + 0.5 * dlogit_row[:, None]
     assert (dpost <= bound).all(), f'{tag}: posterior differs by {dpost.max()} beyond the logit-implied bound'
+    if flat:  # north_star: posteriors within 1e-6 absolute, no allowance
+        assert dpost.max(initial=0) <= 1e-6, f'{tag}: posterior differs by {dpost.max()} (flat bar 1e-6)'
     # argmax identical except ties within 1e-6
     ga, wa = np.argmax(got_post, axis=1), np.argmax(want_post, axis=1)
     for b in np.flatnonzero(ga != wa):
@@ -123,7 +131,8 @@ def test_predict_posteriors_vs_reference_fixture(D, name, flavour):
     assert logits_df.index.name == 'BARCODE' and probs_df.index.name == 'BARCODE'
     assert logits_df.values.dtype == np.float32 and probs_df.values.dtype == np.float32
     check_logits_and_posteriors(f'predict/{name}/{flavour}', logits_df.values, case.fx['predict_logits'],
-                                probs_df.values, case.fx['predict_post'])
+                                probs_df.values, case.fx['predict_post'],
+                                flat=reference_rounding(flavour, case.genotypes.n_genotypes, case.doublet_prior))
 
 
 @pytest.mark.parametrize('flavour', FLAVOURS)
@@ -148,8 +157,10 @@ def test_learn_genotypes_vs_reference_fixture(D, name, flavour):
     assert len(stages) == case.n_iterations
     for it, (df, dbg) in enumerate(stages):
         assert set(dbg) == {'barcode_logits', 'genotype_prior', 'genotype_addition'}
+        # iteration 0 sees identical tables; later ones inherit the (tiny) differences of the learnt additions
         check_logits_and_posteriors(f'staged/{name}/{flavour}/it{it}', dbg['barcode_logits'], fx['stage_logits'][it],
-                                    df.values, fx['stage_post'][it])
+                                    df.values, fx['stage_post'][it], flat=it == 0 and reference_rounding(
+                                        flavour, case.genotypes.n_genotypes, case.doublet_prior))
         # the addition only ever acts through betas_reg + addition (demux.py:90), betas_reg >= default_prior
         total = fx['betas_reg_learn'].astype(np.float64) + fx['stage_addition'][it]
         add_rel = np.abs(dbg['genotype_addition'].astype(np.float64) - fx['stage_addition'][it]) / total
@@ -278,7 +289,8 @@ def test_shapes_vs_oracle(D, shape, flavour):
         ol, op = O.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=dp)
         gl, gp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=dp)
         assert list(gl.columns) == list(ol.columns)
-        check_logits_and_posteriors(f'shape/G{G}/dp{dp}/{flavour}', gl.values, ol.values, gp.values, op.values)
+        check_logits_and_posteriors(f'shape/G{G}/dp{dp}/{flavour}', gl.values, ol.values, gp.values, op.values,
+                                    flat=reference_rounding(flavour, G, dp))
     n_it = 3 if G >= 64 else 10
     og, opost = O.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it, doublet_prior=0.35 if G < 200 else 0.)
     gg, gpost = D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=n_it, doublet_prior=0.35 if G < 200 else 0.)
@@ -323,20 +335,22 @@ def test_warp_pair_kernel_widths_and_segments(D, native_lib, shape, seg_rows):
     import torch
     ds = make_dataset(**shape)
     G = shape['n_genotypes']
-    D.estep_flavour = 'fast'
-    assert native_lib.dmx_estep_plan_supported(G, 0.35, 1) == 1
+    D.estep_flavour = 'auto'
+    assert native_lib.dmx_estep_plan_supported(G, 0.35, 2) == 1
     O = oracle.OracleDemultiplexer
     ol, op = O.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.35)
     old = D.estep_segment_rows
     try:
         D.estep_segment_rows = seg_rows
         gl, gp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.35)
-        check_logits_and_posteriors(f'warp/G{G}/seg{seg_rows}', gl.values, ol.values, gp.values, op.values)
+        check_logits_and_posteriors(f'warp/G{G}/seg{seg_rows}', gl.values, ol.values, gp.values, op.values,
+                                    flat=reference_rounding('auto', G, 0.35))
         if G <= 8:  # the lane-per-row kernel also serves the singlet-only E-step
-            assert native_lib.dmx_estep_plan_supported(G, 0.0, 1) == 1
+            assert native_lib.dmx_estep_plan_supported(G, 0.0, 2) == 1
             sl, sp = O.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.)
             tl, tp = D.predict_posteriors(ds.calls, ds.genotypes, ds.barcode_handler, doublet_prior=0.)
-            check_logits_and_posteriors(f'warp/G{G}/seg{seg_rows}/dp0', tl.values, sl.values, tp.values, sp.values)
+            check_logits_and_posteriors(f'warp/G{G}/seg{seg_rows}/dp0', tl.values, sl.values, tp.values, sp.values,
+                                        flat=True)
         # the plan itself: every barcode appears in ceil(rows / seg_rows) consecutive items (at least one)
         pack = D._pack_device(ds.calls, ds.genotypes, ds.barcode_handler.n_barcodes, add_data_prior=False)
         seg_prefix, item_slot, n_items, _ = D._estep_plan(pack, 0.35)
@@ -426,22 +440,29 @@ def test_barcode_sharding_is_consistent(D):
     halves = [D._pack_device(case.calls, case.genotypes, B, add_data_prior=True, barcode_range=r)
               for r in ((0, B // 3), (B // 3, B))]
     assert sum(h.n_rows for h in halves) == full.n_rows
-    for h in halves:
-        assert np.array_equal(h.n_mol.cpu().numpy(), full.n_mol.cpu().numpy())  # data prior sees every call
-        assert np.array_equal(bits(h.betas.cpu().numpy()), bits(full.betas.cpu().numpy()))
+    # the data prior counts the molecules of every shard (summed by an integer all-reduce in a multi-GPU run)
+    assert np.array_equal(sum(h.n_mol.cpu().numpy() for h in halves), full.n_mol.cpu().numpy())
+    # rows of the shards = rows of the whole pack, barcode ids local to the range
+    full_cb, full_v, full_e = (t.cpu().numpy() for t in (full.csc_cb, full.csc_variant, full.csc_e))
+    for h, (a, b) in zip(halves, ((0, B // 3), (B // 3, B))):
+        assert h.n_barcodes == b - a and h.barcode_range == (a, b)
+        mine = (full_cb >= a) & (full_cb < b)
+        assert np.array_equal(h.csc_cb.cpu().numpy(), full_cb[mine] - a)
+        assert np.array_equal(h.csc_variant.cpu().numpy(), full_v[mine])
+        assert np.array_equal(bits(h.csc_e.cpu().numpy()), bits(full_e[mine]))
     table = D._probs_table(full, None, 0.01)
     fl, fp, fs = D._e_step(full, table, 0.35, want_singlets=True)
     lo = 0
     parts64 = []
     for h, (a, b) in zip(halves, ((0, B // 3), (B // 3, B))):
         hl, hp, hs = D._e_step(h, table, 0.35, want_singlets=True)
-        assert np.array_equal(bits(hl.cpu().numpy()[a:b]), bits(fl.cpu().numpy()[a:b]))
+        assert np.array_equal(bits(hl.cpu().numpy()), bits(fl.cpu().numpy()[a:b]))
         out64 = torch.zeros((full.n_variants, full.n_genotypes), dtype=torch.float64, device='cuda')
         out32 = torch.zeros((full.n_variants, full.n_genotypes), dtype=torch.float32, device='cuda')
         from demuxalot_b200 import _native
         lib = _native.load()
-        assert lib.dmx_mstep(h.variant_offsets.data_ptr(), h.csc_cb.data_ptr(), h.csc_e.data_ptr(), fs.data_ptr(),
-                             fs.shape[1], full.n_genotypes, 2.0, out32.data_ptr(), full.n_genotypes,
+        assert lib.dmx_mstep(h.variant_offsets.data_ptr(), h.csc_cb.data_ptr(), h.csc_e.data_ptr(),
+                             fs[a:b].data_ptr(), fs.shape[1], full.n_genotypes, 2.0, out32.data_ptr(), full.n_genotypes,
                              out64.data_ptr(), full.n_genotypes, 0, full.n_variants,
                              torch.cuda.current_stream().cuda_stream) == 0
         parts64.append(out64)
@@ -464,6 +485,6 @@ def test_float64_prior_logits_are_added_like_numpy(D, dp):
         base = list(D.staged_genotype_learning(case.calls, case.genotypes, case.barcode_handler, n_iterations=1,
                                                doublet_prior=dp))[0][1]['barcode_logits']
     finally:
-        D.estep_flavour = 'fast'
+        D.estep_flavour = 'auto'
     want = (base.astype(np.float64) + prior).astype(np.float32)  # numpy's in-place `logits += prior`
     assert np.array_equal(bits(got), bits(want))

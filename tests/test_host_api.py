@@ -24,7 +24,7 @@ def test_abi_library_exports_every_declared_symbol(native_lib):
     assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
     for name in declared:
         assert hasattr(native_lib, name), name
-    assert native_lib.dmx_abi_version() == _native.ABI_VERSION == 3
+    assert native_lib.dmx_abi_version() == _native.ABI_VERSION == 4
     # size queries are pure host functions: callable without a GPU
     assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.25, 0, 1) >= 10 * 10 * 4
     assert native_lib.dmx_estep_workspace_bytes(10, 4, 0.0, 0, 1) >= 10 * 4 * 4
