@@ -137,6 +137,14 @@ def pin(array: np.ndarray) -> bool:
     return int(rc) == 0
 
 
+def unpin(array: np.ndarray) -> None:
+    """cudaHostUnregister: a registered buffer must be unregistered BEFORE numpy frees it -- otherwise the driver keeps
+    the stale mapping and a later pageable copy out of recycled addresses fails with cudaErrorAlreadyMapped."""
+    import torch
+    if array.nbytes:
+        torch.cuda.cudart().cudaHostUnregister(array.ctypes.data)
+
+
 def slice_barcodes(ds, n_b: int):
     """First n_b barcodes of a dataset as a self-contained (calls, barcode_handler) pair."""
     from demuxalot_b200 import BarcodeHandler, CompressedSNPCalls
@@ -767,6 +775,11 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                       f'process as the reference is written): value = table + E-step + softmax on packed rows '
                       f'({t_step:.1f} s), e2e_value adds pack_calls ({t_pack:.1f} s); host has {os.cpu_count()} logical cores',
         }
+    if pinned:
+        for c in ds.calls.values():
+            unpin(c.snp_calls)
+            unpin(c.molecules)
+        unpin(ds.genotypes.variant_betas)
     del ds
     if not args.no_extras:
         extras_scale = args.scale
