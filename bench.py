@@ -340,8 +340,24 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
     if ctx.world > 1:
         D.process_group = dist.group.WORLD
     try:
+        if ctx.world > 1:  # NCCL opens its point-to-point channels on first use: not part of a pack
+            warm = torch.zeros(ctx.world * 4, dtype=torch.int32, device=ctx.dev)
+            dist.all_to_all_single(torch.empty_like(warm), warm)
+            dist.all_reduce(warm)
         pack_s, pack = ctx.wall(lambda: D._pack_device(None, ds.genotypes, B, add_data_prior=True, shard=shard,
                                                        device_parts=[part], keep_calls=False))
+        # the same pack once more with a synchronisation after every stage (stage times; the sum is a little longer)
+        pack_rows = pack.n_rows
+        del pack
+        torch.cuda.empty_cache()
+        D.pack_profile = {}
+        try:
+            pack = D._pack_device(None, ds.genotypes, B, add_data_prior=True, shard=shard, device_parts=[part],
+                                  keep_calls=False)
+            pack_stages = {k: ctx.max(v) for k, v in sorted(D.pack_profile.items())}
+        finally:
+            D.pack_profile = None
+        assert pack.n_rows == pack_rows
         del part
         torch.cuda.empty_cache()
         rows_total = ctx.sum(pack.n_rows)
@@ -363,7 +379,7 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
             'donors': G, 'columns': C, 'variants': pack.n_variants, 'barcodes': B,
             'molecule_calls': int(calls_total), 'read_rows': int(rows_total), 'em_iterations': n_it,
             'host_genotypes_s': round(t_host, 2), 'host_index_s': round(t_index, 2),
-            'pack_s': pack_s, 'pack_rows_per_s': rows_total / pack_s,
+            'pack_s': pack_s, 'pack_rows_per_s': rows_total / pack_s, 'pack_stages': pack_stages,
             'em_s': em_s, 'ms_per_iteration': 1e3 * em_s / n_it, 'iterations_per_s': n_it / em_s,
             'updates_per_s': rows_total * C * n_it / em_s,
             'what': 'pack = match + histogram + route + all-to-all + sort of the shard (inputs resident in HBM); '

@@ -14,7 +14,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / 'csrc'
 LIB_PATH = CSRC / 'libdemux_b200.so'
-SOURCES = ['api.cu', 'builder.cu', 'table.cu', 'estep.cu', 'estep_pairs.cu', 'estep_pairs_warp.cu', 'mstep.cu',
+SOURCES = ['api.cu', 'builder.cu', 'table.cu', 'estep.cu', 'estep_pairs.cu', 'estep_pairs_warp.cu', 'estep_pairs_strip.cu', 'mstep.cu',
            'snp_aggregate.cu', 'comm.cu']
 HEADERS = [CSRC / 'common.cuh', CSRC.parent.parent / 'include' / 'demux_b200.h']
 

@@ -860,11 +860,20 @@ float pair_doublet_bonus(int n_genotypes, double dp) {  // demux.py:168-172
     return (float)bonus;
 }
 
+// estep_pairs_strip.cu
+bool estep_pairs_strip_supported(int G);
+int launch_estep_pairs_strip(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* seg_prefix,
+                             const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
+                             const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
+                             float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
+                             int64_t ld_logits, double* partial, int64_t n_cols, cudaStream_t stream);
+
 bool estep_pairs_warp_supported(int G, int flavour) {
     if (warp_env_int("DMX_PAIRS_WARP", 1) == 0) return false;
     const int nb = (G + 7) / 8;
     if (G <= 8) return warp_env_int("DMX_PAIRS_SMALL", 1) != 0;  // lane-per-row kernel, both flavours
     if (flavour != DMX_ESTEP_FAST) return false;
+    if (G > 16 && estep_pairs_strip_supported(G)) return true;  // strip kernel: 25..32 and 57..64 genotypes
     if (nb == 2) return true;                                    // 3 tiles x 10 row groups
     if (nb == 3 || nb == 4 || nb == 5 || nb == 7) return true;  // lane utilisation >= 28 / 32
     return patch_kernel_supported(G);                            // other widths: estep_pairs.cu
@@ -930,6 +939,10 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
     // 9 <= G <= 16: 3 tiles x 10 row groups, 8-row chunks with a flush per chunk (not FP32 bound at this width).  Measured
     // at G = 16, 20 M rows: 0.47 ms against 0.81 ms for the CTA kernel and 0.73 ms for a lane-pair-per-row kernel (dropped)
     if (G <= 16) return launch_warp_variant<2, 8, 8, false, 168, true>(p, n_items, stream);
+    if (estep_pairs_strip_supported(G))
+        return launch_estep_pairs_strip(barcode_offsets, barcode_order, seg_prefix, item_slot, n_items, seg_rows,
+                                        csr_variant, csr_e, table, ld_table, G, doublet_prior, table_floor, prior_logits,
+                                        ld_prior, logits, ld_logits, partial, n_cols, stream);
     const int variant = warp_env_int("DMX_WARP_VARIANT", 0);  // experiments: exponent packing / occupancy target
 #define DMX_WARP(NB_, SR_, ESM_, REGS_, PF_)                                                                   \
     return long_products ? launch_warp_variant<NB_, 16, SR_, ESM_, REGS_, PF_>(p, n_items, stream)            \

@@ -204,6 +204,7 @@ class Demultiplexer:
     # variant-range tiles of the sharded M-step: all-reduce of tile k overlaps the M-step of tile k + 1.  Measured
     # (profiles/r01_allreduce_sweep_*.json): the 168 MB all-reduce is 0.34 ms over NVLink, every extra tile costs
     # ~0.25 ms of stream hand-over, so one tile wins; more tiles only pay off for tables of many GB.
+    pack_profile: Optional[dict] = None  # set to a dict to receive the wall time of the pack stages (synchronises)
     mstep_allreduce_tiles = 2
     # 'float64': reduce-scatter of float64 partials, one rounding after the global sum (N GPUs give the bits of one up
     # to float64 regrouping), all-gather of float32; 'float32': float32 all-reduce, half the bytes again at the price of
@@ -525,14 +526,28 @@ class Demultiplexer:
         dev = cls._device()
         index = cls._genotype_index(genotypes)
         n_variants = genotypes.n_variants
+        profile = cls.pack_profile
+        clock = [None]
+
+        def lap(name):  # only when profiling: one synchronisation per stage
+            if profile is not None:
+                import time
+                torch.cuda.synchronize(dev)
+                now = time.perf_counter()
+                if clock[0] is not None and name:
+                    profile[name] = profile.get(name, 0.0) + now - clock[0]
+                clock[0] = now
+
         with torch.cuda.device(dev):
             dindex = _device_index(index, dev)
+            lap(None)
             if device_parts is not None:
                 call_variant, call_cb, call_e, n_calls = cls._unpack_device_parts(
                     device_parts, dindex, index['chrom2id'], n_variants, dev)
             else:
                 parts = cls._select_parts(chromosome2compressed_snp_calls, index['chrom2id'])
                 call_variant, call_cb, call_e, n_calls = cls._upload_unpack(parts, dindex, n_variants, dev, shard)
+            lap('unpack_match_s')
             if barcode_range is not None:
                 assert shard is None
                 call_variant, call_cb, call_e, n_calls = cls._keep_barcode_range(
@@ -544,8 +559,10 @@ class Demultiplexer:
                 call_variant, call_cb, call_e, n_calls, barcode_range = cls._route_calls(
                     call_variant, call_cb, call_e, n_calls, n_variants, n_barcodes, shard, dev)
                 n_barcodes = barcode_range[1] - barcode_range[0]
+            lap('route_exchange_s')
             pack = cls._finish_pack(call_variant, call_cb, call_e, n_calls, genotypes, index, dindex, n_barcodes,
                                     add_data_prior, dev, barcode_range)
+            lap('rows_and_prior_s')
             if not keep_calls:  # only pack_calls() and the aggregate_on_snps branch read the molecule-level calls
                 pack.call_variant = pack.call_cb = pack.call_e = None
         return pack

@@ -267,7 +267,8 @@ def make_device_dataset(n_genotypes: int, n_snps: int, n_barcodes: int, rows_per
 
 DEVICE_CONFIGS = {
     # BASELINE.json configs[3]
-    'biobank_200': dict(n_genotypes=200, n_snps=2_500_000, n_barcodes=100_000, rows_per_barcode=5000),
+    # rows_per_barcode counts (SNP, barcode) groups: ~1.2 (variant, barcode) rows each -> ~500 M read rows
+    'biobank_200': dict(n_genotypes=200, n_snps=2_500_000, n_barcodes=100_000, rows_per_barcode=4050),
 }
 
 

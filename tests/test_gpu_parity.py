@@ -316,7 +316,12 @@ WARP_SHAPES = [
     dict(n_genotypes=16, n_snps=1200, n_barcodes=100, rows_per_barcode=800, seed=47),
     dict(n_genotypes=17, n_snps=500, n_barcodes=60, rows_per_barcode=150, seed=31),
     dict(n_genotypes=24, n_snps=900, n_barcodes=50, rows_per_barcode=260, seed=32, empty_barcode_fraction=0.2),
+    # strip kernel (25..32 and 57..64 genotypes), incl. widths whose table rows are narrower than the padded width
+    dict(n_genotypes=27, n_snps=1200, n_barcodes=60, rows_per_barcode=333, seed=51, empty_barcode_fraction=0.2),
     dict(n_genotypes=30, n_snps=2500, n_barcodes=120, rows_per_barcode=700, seed=33, shuffle_variants=True),
+    dict(n_genotypes=32, n_snps=2000, n_barcodes=80, rows_per_barcode=900, seed=52),
+    dict(n_genotypes=58, n_snps=1500, n_barcodes=30, rows_per_barcode=260, seed=53, shuffle_variants=True),
+    dict(n_genotypes=64, n_snps=1800, n_barcodes=40, rows_per_barcode=420, seed=54),
     dict(n_genotypes=37, n_snps=1200, n_barcodes=40, rows_per_barcode=180, seed=34),
     dict(n_genotypes=53, n_snps=1500, n_barcodes=30, rows_per_barcode=120, seed=35),
     # patch kernel (a warp per 32-tile patch of the triangle): 10, 18, 21 and 25 blocks of 8 genotypes
