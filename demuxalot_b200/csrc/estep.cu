@@ -30,12 +30,20 @@ int launch_estep_pairs(const int64_t* barcode_offsets, const int32_t* barcode_or
                        int64_t ld_logits, int flavour, cudaStream_t stream);
 
 // estep_pairs_warp.cu
+struct FusedSoftmax {
+    float* post;
+    int64_t ld_post;
+    float* singlets;
+    int64_t ld_singlet;
+    bool logits_requested;
+};
 bool estep_pairs_warp_supported(int G, int flavour);
 int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barcode_order, const int32_t* seg_prefix,
                             const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
                             const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
                             float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
-                            int64_t ld_logits, double* partial, int64_t n_cols, int flavour, cudaStream_t stream);
+                            int64_t ld_logits, double* partial, int64_t n_cols, int flavour, const FusedSoftmax* fused,
+                            int* did_fuse, cudaStream_t stream);
 float pair_doublet_bonus(int n_genotypes, double dp);
 int launch_plan_segments(const int64_t* offsets, const int32_t* order, int64_t n_barcodes, int seg_rows,
                          int32_t* n_seg, cudaStream_t stream);
@@ -171,6 +179,7 @@ struct CombineParams {
     int n_singlets;
     float doublet_bonus;
     double scale;  // partial sums are log2-sums (ln 2) or natural-log sums (1)
+    int skip_single;  // single-item barcodes were finished (softmax included) by the pair kernel itself
 };
 
 // DMX_ESTEP_AUTO: the reference's roundings wherever the E-step waits on the row stream and they are (nearly) free --
@@ -192,6 +201,7 @@ __global__ void __launch_bounds__(128) softmax_rows_kernel(float* __restrict__ l
         const int seg_first = cp.seg_prefix[blockIdx.x];
         const int n_seg = cp.seg_prefix[blockIdx.x + 1] - seg_first;
         if (cp.order) barcode = cp.order[blockIdx.x];
+        if (n_seg == 1 && cp.skip_single) return;
         if (n_seg > 1) {  // every thread later re-reads only the columns it writes here
             float* out = logits + barcode * ld_logits;
             for (int c = threadIdx.x; c < n_cols; c += blockDim.x) {
@@ -379,13 +389,17 @@ int dmx_estep(const int64_t* barcode_offsets, const int32_t* barcode_order, cons
                                                   csr_e, table, ld_table, G, prior_logits, ld_prior, out_logits, ld_out);
         if (rc) return rc;
     } else if (planned) {
+        FusedSoftmax fused = {posteriors, ld_post, singlet_posteriors, ld_singlet, logits != nullptr};
+        int did_fuse = 0;
         const int rc = launch_estep_pairs_warp(barcode_offsets, barcode_order, seg_prefix, item_slot, n_items, seg_rows,
                                                csr_variant, csr_e, table, ld_table, G, doublet_prior, table_floor,
                                                prior_logits, ld_prior, out_logits, ld_out, partial, n_cols, flavour,
-                                               stream);
+                                               &fused, &did_fuse, stream);
         if (rc) return rc;
+        if (did_fuse && !partial) return 0;  // every barcode was a single work item: nothing left to do
         if (partial) {
             CombineParams cp;
+            cp.skip_single = did_fuse;
             cp.order = barcode_order;
             cp.seg_prefix = seg_prefix;
             cp.partial = partial;

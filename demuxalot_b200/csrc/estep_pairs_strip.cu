@@ -57,6 +57,13 @@ struct StripParams {
     double* partial;
     int64_t n_cols;
     unsigned mant_mask, one_bits;
+    // fused row softmax (demux.py:101,152) for barcodes that are a single work item: the warp that owns the barcode
+    // keeps its float32 logits in shared memory and writes the posteriors itself
+    float* post;       // [B, ld_post] or nullptr
+    int64_t ld_post;
+    float* singlets;   // [B, ld_singlet] or nullptr
+    int64_t ld_singlet;
+    int fuse_softmax;
 };
 
 __device__ __forceinline__ uint64_t spack2(float lo, float hi) {
@@ -127,7 +134,8 @@ __global__ void __maxnreg__(MAX_REGS) estep_pairs_strip_kernel(const StripParams
     constexpr int DUMP_LD = 33;
     constexpr float SCALE = CPF == 2 ? 4.f : 1.f;   // operands are staged times SCALE (exact), removed in the epilogue
     constexpr int STAGE_FLOATS = 2 * CHUNK * LD;
-    constexpr int DUMP_FLOATS = 2 * STRIP_NP * DUMP_LD;
+    constexpr int C_MAX = GP * (GP + 1) / 2;        // logits of one barcode (fused softmax)
+    constexpr int DUMP_FLOATS = 2 * STRIP_NP * DUMP_LD + C_MAX;
     constexpr int SMEM_FLOATS = STAGE_FLOATS > DUMP_FLOATS ? STAGE_FLOATS : DUMP_FLOATS;
     __shared__ __align__(16) float smem[SMEM_FLOATS];
     float* const stage0 = smem;
@@ -368,6 +376,8 @@ __global__ void __maxnreg__(MAX_REGS) estep_pairs_strip_kernel(const StripParams
     const double padded_rows = (double)n_chunks * (double)CHUNK * (CPF == 2 ? 3.0 : 1.0);
     float* const dump_l = smem;
     unsigned* const dump_e = reinterpret_cast<unsigned*>(smem + STRIP_NP * DUMP_LD);
+    float* const logits_s = smem + 2 * STRIP_NP * DUMP_LD;
+    const bool fuse = p.fuse_softmax && n_seg == 1;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -398,12 +408,28 @@ __global__ void __maxnreg__(MAX_REGS) estep_pairs_strip_kernel(const StripParams
                 const float pen = (i == j) ? 0.f : p.doublet_bonus;
                 float logit = (float)((double)pen + sum * 0.693147180559945309417232);
                 if (p.prior) logit = (float)((double)logit + p.prior[barcode * p.ld_prior + col]);
-                p.logits[barcode * p.ld_logits + col] = logit;
+                if (p.logits) p.logits[barcode * p.ld_logits + col] = logit;
+                if (fuse) logits_s[col] = logit;
             } else {
                 p.partial[(int64_t)item * p.n_cols + col] = sum;
             }
         }
         __syncwarp();
+    }
+    if (fuse) {  // same arithmetic as softmax_rows_kernel (estep.cu): float32 max and exp, float64 sum, float32 divide
+        const int n_cols = (int)p.n_cols;
+        float m = -3.402823466e+38f;
+        for (int c = lane; c < n_cols; c += 32) m = fmaxf(m, logits_s[c]);
+        m = warp_max(m);
+        double sum = 0.0;
+        for (int c = lane; c < n_cols; c += 32) sum += (double)expf(__fsub_rn(logits_s[c], m));
+        sum = warp_sum(sum);
+        const float total = (float)sum;
+        for (int c = lane; c < n_cols; c += 32) {
+            const float pr = __fdiv_rn(expf(__fsub_rn(logits_s[c], m)), total);
+            if (p.post) p.post[barcode * p.ld_post + c] = pr;
+            if (p.singlets && c < G) p.singlets[barcode * p.ld_singlet + c] = pr;
+        }
     }
 }
 
@@ -511,7 +537,8 @@ int launch_estep_pairs_strip(const int64_t* barcode_offsets, const int32_t* barc
                              const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
                              const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
                              float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
-                             int64_t ld_logits, double* partial, int64_t n_cols, cudaStream_t stream) {
+                             int64_t ld_logits, double* partial, int64_t n_cols, float* post, int64_t ld_post,
+                             float* singlets, int64_t ld_singlet, cudaStream_t stream) {
     DMX_REQUIRE(seg_rows >= 16 && seg_rows <= 4096, "seg_rows %d outside [16, 4096]", seg_rows);
     DMX_REQUIRE(n_items > 0 && n_items < (1ll << 31), "bad item count %lld", (long long)n_items);
     const int nb = (G + 7) / 8;
@@ -541,6 +568,11 @@ int launch_estep_pairs_strip(const int64_t* barcode_offsets, const int32_t* barc
     p.n_cols = n_cols;
     p.mant_mask = 0x007fffffu;
     p.one_bits = 0x3f800000u;
+    p.post = post;
+    p.ld_post = ld_post;
+    p.singlets = singlets;
+    p.ld_singlet = ld_singlet;
+    p.fuse_softmax = (post || singlets) ? 1 : 0;
     // factors lie in [2 (floor + 1e-4), 2.0002]: 8 of them always keep a product normal, 16 need floor >= 0.0027, and 32
     // (operands staged times 4: factors in [0.077, 8.001]) need floor >= 0.0095 -- the default clip is 0.01
     const int period_env = getenv("DMX_STRIP_PERIOD") ? atoi(getenv("DMX_STRIP_PERIOD")) : 32;

@@ -30,6 +30,15 @@ static int warp_env_int(const char* name, int fallback) {
     return (v && *v) ? atoi(v) : fallback;
 }
 
+// outputs of the row softmax when the pair kernel takes it over for single-item barcodes (estep_pairs_strip.cu)
+struct FusedSoftmax {
+    float* post;
+    int64_t ld_post;
+    float* singlets;
+    int64_t ld_singlet;
+    bool logits_requested;  // false: the logits only live in the workspace, nobody reads the rows of fused barcodes
+};
+
 struct WarpPairsParams {
     const int64_t* offsets;     // barcode_offsets [B + 1]
     const int32_t* order;       // schedule slot -> barcode, or nullptr (identity)
@@ -400,9 +409,13 @@ __host__ __device__ inline void patch_tile(int nb, int g, int* ti, int* tj) {
     *ti = *tj = nb - 1;
 }
 
-template <int FLUSH_ROWS>
-__global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams p, int nb, int n_tiles, int n_patches) {
-    constexpr int CHUNK = FLUSH_ROWS;  // one row group: rows per staged chunk = rows per flush (<= 16)
+// CPF: staged chunks per flush.  2: the operands are staged times 4 (exact) so that 32 factors in [0.077, 8.001] keep a
+// product normal (needs table entries >= 0.0095; the default clip is 0.01) -- half the flush instructions; the flush is
+// exact, so its period does not change any result bit.
+template <int FLUSH_ROWS, int CPF, int MAX_REGS = 168>
+__global__ void __maxnreg__(MAX_REGS) estep_pairs_patch_kernel(const WarpPairsParams p, int nb, int n_tiles, int n_patches) {
+    constexpr int CHUNK = FLUSH_ROWS;  // one row group: rows per staged chunk (<= 16)
+    constexpr float SCALE = CPF == 2 ? 4.f : 1.f;
     constexpr int LD = PATCH_LD;
     constexpr int DUMP_LD = 33;
     constexpr int STAGE_FLOATS = 2 * CHUNK * LD;
@@ -501,7 +514,7 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
 #pragma unroll
                         for (int u = 0; u < 2; ++u) {
                             if (live && 2 * b + u < n_table_quads) cp_async_16(dst + 8 * t + 4 * u, src + 4 * u);
-                            else *reinterpret_cast<float4*>(dst + 8 * t + 4 * u) = make_float4(1.f, 1.f, 1.f, 1.f);
+                            else *reinterpret_cast<float4*>(dst + 8 * t + 4 * u) = make_float4(SCALE, SCALE, SCALE, SCALE);
                         }
                     }
                 }
@@ -513,8 +526,8 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
         cp_async_wait<0>();
         if (live) {  // columns past the table width hold 1 and get transformed too: no pair that uses them is written
             float* dst = buf + row_in_chunk * LD + 8 * k0;
-            const float w = __fsub_rn(1.f, e_cur);
-            const float ef = fmaxf(e_cur, WARP_ERROR_FLOOR);
+            const float w = __fmul_rn(__fsub_rn(1.f, e_cur), SCALE);
+            const float ef = __fmul_rn(fmaxf(e_cur, WARP_ERROR_FLOOR), SCALE);
             // two blocks per batch: all loads of a batch first (the operand registers of the row loop are dead
             // here), so the fma chains do not each wait for their own shared-memory round trip
 #pragma unroll
@@ -548,6 +561,7 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
     }
     __syncwarp();
 
+    int n_flushes = 0;
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
         float* cur = (chunk & 1) ? stage1 : stage0;
         float* nxt = (chunk & 1) ? stage0 : stage1;
@@ -580,26 +594,30 @@ __global__ void __maxnreg__(168) estep_pairs_patch_kernel(const WarpPairsParams 
             }
             i_lo = n_i_lo; i_hi = n_i_hi; j_lo = n_j_lo; j_hi = n_j_hi;
         }
+        if (CPF == 1 || (chunk & 1)) {
+            ++n_flushes;
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                float lo, hi;
-                wunpack2(prod[a][b], lo, hi);
-                const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
-                esum[a][b] += blo >> 23;
-                esum[a][b] += (bhi >> 23) << 16;
-                prod[a][b] = wpack2(__uint_as_float(wreset_mantissa(blo, mant_mask, one_bits)),
-                                    __uint_as_float(wreset_mantissa(bhi, mant_mask, one_bits)));
-            }
+                for (int b = 0; b < 8; ++b) {
+                    float lo, hi;
+                    wunpack2(prod[a][b], lo, hi);
+                    const unsigned blo = __float_as_uint(lo), bhi = __float_as_uint(hi);
+                    esum[a][b] += blo >> 23;
+                    esum[a][b] += (bhi >> 23) << 16;
+                    prod[a][b] = wpack2(__uint_as_float(wreset_mantissa(blo, mant_mask, one_bits)),
+                                        __uint_as_float(wreset_mantissa(bhi, mant_mask, one_bits)));
+                }
+        }
         if (more) land(nxt);
         __syncwarp();
     }
 
     // ---- epilogue (see the warp kernel): dump, then a rolled lane-parallel walk over the patch's pairs -------------
     const int G = p.n_genotypes;
-    const int bias = 127 * n_chunks;
-    const double padded_rows = (double)n_chunks * (double)CHUNK;
+    const int bias = 127 * n_flushes;
+    // every staged row carries the 2 of the pair sum and SCALE: log2(2 SCALE) = 3 per row when SCALE = 4
+    const double padded_rows = (double)n_chunks * (double)CHUNK * (CPF == 2 ? 3.0 : 1.0);
     unsigned* const dump_e = reinterpret_cast<unsigned*>(smem + 32 * DUMP_LD);
     float* const dump_l = smem;
 #pragma unroll
@@ -866,7 +884,8 @@ int launch_estep_pairs_strip(const int64_t* barcode_offsets, const int32_t* barc
                              const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
                              const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
                              float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
-                             int64_t ld_logits, double* partial, int64_t n_cols, cudaStream_t stream);
+                             int64_t ld_logits, double* partial, int64_t n_cols, float* post, int64_t ld_post,
+                             float* singlets, int64_t ld_singlet, cudaStream_t stream);
 
 bool estep_pairs_warp_supported(int G, int flavour) {
     if (warp_env_int("DMX_PAIRS_WARP", 1) == 0) return false;
@@ -893,7 +912,9 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
                             const int32_t* item_slot, int64_t n_items, int seg_rows, const int32_t* csr_variant,
                             const float* csr_e, const float* table, int64_t ld_table, int G, double doublet_prior,
                             float table_floor, const double* prior_logits, int64_t ld_prior, float* logits,
-                            int64_t ld_logits, double* partial, int64_t n_cols, int flavour, cudaStream_t stream) {
+                            int64_t ld_logits, double* partial, int64_t n_cols, int flavour, const FusedSoftmax* fused,
+                            int* did_fuse, cudaStream_t stream) {
+    if (did_fuse) *did_fuse = 0;
     DMX_REQUIRE(seg_rows >= 16 && seg_rows <= 4096, "seg_rows %d outside [16, 4096]", seg_rows);
     DMX_REQUIRE(n_items > 0 && n_items < (1ll << 31), "bad item count %lld", (long long)n_items);
     WarpPairsParams p;
@@ -939,10 +960,17 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
     // 9 <= G <= 16: 3 tiles x 10 row groups, 8-row chunks with a flush per chunk (not FP32 bound at this width).  Measured
     // at G = 16, 20 M rows: 0.47 ms against 0.81 ms for the CTA kernel and 0.73 ms for a lane-pair-per-row kernel (dropped)
     if (G <= 16) return launch_warp_variant<2, 8, 8, false, 168, true>(p, n_items, stream);
-    if (estep_pairs_strip_supported(G))
+    if (estep_pairs_strip_supported(G)) {
+        // the warp that owns a single-item barcode also takes its softmax (fused), and then only writes the logits when
+        // the caller asked for them
+        const bool fuse = fused && (fused->post || fused->singlets) && warp_env_int("DMX_FUSE_SOFTMAX", 1) != 0;
+        if (fuse && did_fuse) *did_fuse = 1;
         return launch_estep_pairs_strip(barcode_offsets, barcode_order, seg_prefix, item_slot, n_items, seg_rows,
                                         csr_variant, csr_e, table, ld_table, G, doublet_prior, table_floor, prior_logits,
-                                        ld_prior, logits, ld_logits, partial, n_cols, stream);
+                                        ld_prior, fuse && !fused->logits_requested ? nullptr : logits, ld_logits, partial,
+                                        n_cols, fuse ? fused->post : nullptr, fuse ? fused->ld_post : 0,
+                                        fuse ? fused->singlets : nullptr, fuse ? fused->ld_singlet : 0, stream);
+    }
     const int variant = warp_env_int("DMX_WARP_VARIANT", 0);  // experiments: exponent packing / occupancy target
 #define DMX_WARP(NB_, SR_, ESM_, REGS_, PF_)                                                                   \
     return long_products ? launch_warp_variant<NB_, 16, SR_, ESM_, REGS_, PF_>(p, n_items, stream)            \
@@ -966,13 +994,24 @@ int launch_estep_pairs_warp(const int64_t* barcode_offsets, const int32_t* barco
         patch_shape(nb, &n_tiles, &n_patches, &max_blocks);
         const int64_t grid = n_items * n_patches;
         DMX_REQUIRE(grid < (1ll << 31), "grid too large");
-        if (long_products) {
-            auto kernel = estep_pairs_patch_kernel<16>;
+        const bool very_long = long_products && table_floor >= 0.0095f && warp_env_int("DMX_PATCH_PERIOD", 16) >= 32;  // opt-in: ptxas spills
+        if (very_long && warp_env_int("DMX_PATCH_REGS", 168) == 184) {
+            auto kernel = estep_pairs_patch_kernel<16, 2, 184>;
+            DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+            kernel<<<(unsigned)grid, 32, 0, stream>>>(p, nb, n_tiles, n_patches);
+        } else if (very_long) {
+            auto kernel = estep_pairs_patch_kernel<16, 2>;
+            DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                          (int)cudaSharedmemCarveoutMaxShared));
+            kernel<<<(unsigned)grid, 32, 0, stream>>>(p, nb, n_tiles, n_patches);
+        } else if (long_products) {
+            auto kernel = estep_pairs_patch_kernel<16, 1>;
             DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           (int)cudaSharedmemCarveoutMaxShared));
             kernel<<<(unsigned)grid, 32, 0, stream>>>(p, nb, n_tiles, n_patches);
         } else {
-            auto kernel = estep_pairs_patch_kernel<8>;
+            auto kernel = estep_pairs_patch_kernel<8, 1>;
             DMX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                           (int)cudaSharedmemCarveoutMaxShared));
             kernel<<<(unsigned)grid, 32, 0, stream>>>(p, nb, n_tiles, n_patches);
