@@ -299,6 +299,15 @@ def em_loop_on_pack(ctx: Ctx, D, pack, n_iterations: int, doublet_prior: float):
     return ctx.max(a.elapsed_time(b)) / 1e3, post, addition
 
 
+def exchange_mode(D, pack) -> str:
+    """How the M-step partials are summed across the ranks in this run (Demultiplexer.mstep_exchange resolved)."""
+    if D.process_group is None:
+        return 'single GPU'
+    if 'peer' in D._mstep_buffers(pack):
+        return 'peer: dmx_peer_sum_f32 (own reduce-scatter + all-gather kernel over NVLink peer memory, float32 partials)'
+    return f'nccl: dmx_mstep_allreduce ({D.mstep_allreduce_dtype} wire, {D._allreduce_tiles(pack)} tile(s))'
+
+
 def collective_exposed_ms(ctx: Ctx, D, pack, doublet_prior: float, reps: int = 3):
     """M-step alone vs M-step + cross-GPU sum on the same posteriors: (mstep_ms, mstep_allreduce_ms), max over ranks."""
     if ctx.world == 1:
@@ -387,11 +396,11 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
             'learnt_betas_sum': learnt_sum, 'singlet_posterior_mass': post_singlet_mass,
             'barcodes_with_max_posterior_gt_0.9': int(confident),
             'peak_device_memory_gb': ctx.max(torch.cuda.max_memory_allocated() / 1e9),
-            'mstep_wire': D.mstep_allreduce_dtype, 'mstep_tiles': int(D.mstep_allreduce_tiles),
+            'mstep_exchange': exchange_mode(D, pack),
         }
         if exposed is not None:
             local_ms, summed_ms = exposed
-            nbytes = pack.n_variants * G * (12 if D.mstep_allreduce_dtype == 'float64' else 8) * (ctx.world - 1) / ctx.world
+            nbytes = pack.n_variants * G * 8 * (ctx.world - 1) / ctx.world  # float32: slice in from every peer, slice out to every peer
             out['collective'] = {'mstep_alone_ms': local_ms, 'mstep_plus_sum_ms': summed_ms,
                                  'exposed_ms': summed_ms - local_ms, 'bytes_on_wire_per_rank': int(nbytes),
                                  'exposed_frac_of_iteration': (summed_ms - local_ms) / (1e3 * em_s / n_it)}
@@ -523,13 +532,16 @@ def run_multi_gpu_parity(ctx: Ctx, D):
     O = oracle.OracleDemultiplexer
     ds = make_dataset(n_genotypes=12, n_snps=1500, n_barcodes=240, rows_per_barcode=150, seed=41)
     out = {}
-    for wire in ('float64', 'float32'):
-        D.mstep_allreduce_dtype = wire
+    modes = [('peer', 'float32'), ('nccl', 'float64'), ('nccl', 'float32')]
+    saved = (D.mstep_exchange, D.mstep_allreduce_dtype)
+    for exchange, wire in modes:
+        D.mstep_exchange, D.mstep_allreduce_dtype = ('auto' if exchange == 'peer' else 'nccl'), wire
         try:
             learnt, post = learn_genotypes_sharded(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4,
                                                    doublet_prior=DOUBLET_PRIOR)
         finally:
-            D.mstep_allreduce_dtype = 'float64'
+            D.mstep_exchange, D.mstep_allreduce_dtype = saved
+        wire = f'{exchange}_{wire}'
         if ctx.rank == 0:
             single, spost = D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4,
                                               doublet_prior=DOUBLET_PRIOR)
@@ -598,6 +610,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     from demuxalot_b200.demultiplexer import n_options
     D = Demultiplexer
     D.estep_flavour = args.flavour
+    if world > 1 and os.environ.get('DMX_HOST_CORES'):  # this rank's share of the host cores (partition_host_cores)
+        D.host_gather_threads = max(1, min(16, int(os.environ['DMX_HOST_CORES']) // 2))
     sm_count = sm_info(lib, local_rank)
 
     if args.workload != 'pbmc_32':  # another workload as the headline
@@ -666,6 +680,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if world > 1:
             D.process_group = dist.group.WORLD
         mbuf = D._mstep_buffers(pack)
+        em_exchange = exchange_mode(D, pack)
         em_state = {'k': 0}
 
         def em_iteration():
@@ -773,9 +788,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                              'profiles/r02_parity_report.json'},
         'em': {'iterations_per_s': args.steps / (em_total_ms / 1e3), 'ms_per_iteration': em_total_ms / args.steps,
                'updates_per_s': units_per_step * args.steps / (em_total_ms / 1e3),
-               'what': 'table + E-step (singlet posteriors) + M-step' + (
-                   f' + cross-GPU sum (dmx_mstep_allreduce, {D.mstep_allreduce_dtype} wire, {D.mstep_allreduce_tiles} tiles)'
-                   if world > 1 else '')},
+               'what': 'table + E-step (singlet posteriors) + M-step' + (f' + cross-GPU sum ({em_exchange})' if world > 1 else '')},
     }
     del pack, table, buffers, flush_buf
     torch.cuda.empty_cache()
@@ -817,11 +830,29 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
+def partition_host_cores(local_rank: int, local_world: int) -> int:
+    """One contiguous block of the host cores per rank (ranks of a node otherwise pile their numpy / gather threads
+    onto the same cores, and first-touch puts each rank's buffers on the memory node of the cores it runs on).
+    Returns the number of cores of this rank."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(local_world, 1)
+        if local_world > 1 and per >= 1:
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
+            return per
+        return len(cores)
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'ours' and world > 1:
+        n_cores = partition_host_cores(local_rank, int(os.environ.get('LOCAL_WORLD_SIZE', world)))
+        os.environ['DMX_HOST_CORES'] = str(n_cores)
     if args.impl == 'reference':
         run_reference(args, rank)
         return

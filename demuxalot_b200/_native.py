@@ -53,6 +53,7 @@ SIGNATURES = {
     'dmx_route_calls_workspace_bytes': (_i64, [_i64]),
     'dmx_route_calls': (C.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _i32, _ptr, _i64, _ptr, _ptr, _ptr,
                                   C.POINTER(_i64), _ptr]),
+    'dmx_peer_sum_f32': (C.c_int, [_ptr, _ptr, _i32, _i32, _i64, _ptr]),
     'dmx_comm_unique_id': (C.c_int, [_ptr]),
     'dmx_comm_init': (C.c_int, [_ptr, _i32, _i32, C.POINTER(_ptr)]),
     'dmx_comm_destroy': (C.c_int, [_ptr]),

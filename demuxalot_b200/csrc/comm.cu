@@ -73,6 +73,34 @@ struct Comm {
     int rank, world;
 };
 
+// ---- cross-GPU sum over peer memory (NVLink / NVSwitch), no library collective ---------------------------------------
+// Every rank's M-step leaves its float32 partial [v_pad, G] in a buffer that all ranks of the node have mapped (CUDA IPC /
+// fabric handles; the host maps them).  Rank r owns slice r of the flattened table: it loads that slice from every rank's
+// partial (peer loads), adds the values in rank order in float64, rounds once and stores the float32 sum into slice r of
+// EVERY rank's output table (peer stores) -- a reduce-scatter and an all-gather in one pass, deterministic, with the
+// same result bits on all ranks.  The two barriers around it are the host's (device-side signal pads).
+struct PeerPointers {
+    const float* in[16];
+    float* out[16];
+};
+
+template <int WORLD>
+__global__ void __launch_bounds__(256) peer_sum_kernel(const PeerPointers p, int rank, int64_t slice_quads) {
+    const int64_t base = (int64_t)rank * slice_quads;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < slice_quads;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        float4 v[WORLD];
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) v[r] = __ldcg(reinterpret_cast<const float4*>(p.in[r]) + base + q);
+        double x = 0.0, y = 0.0, z = 0.0, w = 0.0;
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) { x += (double)v[r].x; y += (double)v[r].y; z += (double)v[r].z; w += (double)v[r].w; }
+        const float4 sum = make_float4((float)x, (float)y, (float)z, (float)w);
+#pragma unroll
+        for (int r = 0; r < WORLD; ++r) __stcg(reinterpret_cast<float4*>(p.out[r]) + base + q, sum);
+    }
+}
+
 __global__ void round_slice_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n) {
     for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
         out[k] = (float)in[k];
@@ -120,6 +148,36 @@ int dmx_comm_destroy(void* comm) {
     cudaEventDestroy(c->all_done);
     cudaStreamDestroy(c->stream);
     delete c;
+    return 0;
+}
+
+int dmx_peer_sum_f32(const void* const* h_partials, void* const* h_outputs, int32_t rank, int32_t world,
+                     int64_t n_elements, void* stream) {
+    using namespace dmx;
+    DMX_REQUIRE(world >= 1 && world <= 16 && rank >= 0 && rank < world, "bad rank %d / world %d (<= 16)", (int)rank, (int)world);
+    DMX_REQUIRE(n_elements >= 0 && n_elements % (4 * (int64_t)world) == 0,
+                "n_elements %lld must be a multiple of 4 * world", (long long)n_elements);
+    if (n_elements == 0) return 0;
+    PeerPointers p = {};
+    for (int r = 0; r < world; ++r) {
+        DMX_REQUIRE(h_partials[r] && h_outputs[r], "null peer pointer for rank %d", r);
+        DMX_REQUIRE(((uintptr_t)h_partials[r] & 15) == 0 && ((uintptr_t)h_outputs[r] & 15) == 0, "peer buffers must be 16-byte aligned");
+        p.in[r] = (const float*)h_partials[r];
+        p.out[r] = (float*)h_outputs[r];
+    }
+    const int64_t slice_quads = n_elements / 4 / world;
+    int64_t blocks = ceil_div(slice_quads, 256);
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t s = (cudaStream_t)stream;
+#define DMX_PEER(W) case W: peer_sum_kernel<W><<<(int)blocks, 256, 0, s>>>(p, rank, slice_quads); break
+    switch (world) {
+        DMX_PEER(1); DMX_PEER(2); DMX_PEER(3); DMX_PEER(4); DMX_PEER(5); DMX_PEER(6); DMX_PEER(7); DMX_PEER(8);
+        DMX_PEER(9); DMX_PEER(10); DMX_PEER(11); DMX_PEER(12); DMX_PEER(13); DMX_PEER(14); DMX_PEER(15); DMX_PEER(16);
+        default: break;
+    }
+#undef DMX_PEER
+    DMX_LAUNCH_CHECK();
     return 0;
 }
 

@@ -205,11 +205,19 @@ class Demultiplexer:
     # (profiles/r01_allreduce_sweep_*.json): the 168 MB all-reduce is 0.34 ms over NVLink, every extra tile costs
     # ~0.25 ms of stream hand-over, so one tile wins; more tiles only pay off for tables of many GB.
     pack_profile: Optional[dict] = None  # set to a dict to receive the wall time of the pack stages (synchronises)
-    mstep_allreduce_tiles = 2
+    # How the M-step partials of the barcode shards are summed across GPUs:
+    #   'peer': dmx_peer_sum_f32 -- our own reduce-scatter + all-gather kernel over NVLink peer memory (float32 partials
+    #           summed in rank order in float64, one rounding; identical bits on every rank); needs torch symmetric memory
+    #   'nccl': dmx_mstep_allreduce -- NCCL collectives on a second stream, tiled against the M-step kernel
+    #   'auto': 'peer' when the platform offers it, else 'nccl'
+    mstep_exchange = 'auto'
+    # tiles of the NCCL path; 0 = by table size: 1 below 1 GiB (every tile costs a launch tail of the M-step tiers, which
+    # outweighs what it hides: profiles/r02_sweep_mstep_allreduce_n2.json), 4 above
+    mstep_allreduce_tiles = 0
     # 'float64': reduce-scatter of float64 partials, one rounding after the global sum (N GPUs give the bits of one up
     # to float64 regrouping), all-gather of float32; 'float32': float32 all-reduce, half the bytes again at the price of
     # one rounding per shard (~world_size * 6e-8 relative on the addition, far inside the 1e-5 parity bar)
-    mstep_allreduce_dtype = 'float64'
+    mstep_allreduce_dtype = 'float32'
 
     # ------------------------------------------------------------------------------------------------ helpers
     @classmethod
@@ -714,20 +722,38 @@ class Demultiplexer:
         return cached
 
     @classmethod
+    def _allreduce_tiles(cls, pack: DevicePack) -> int:
+        tiles = int(cls.mstep_allreduce_tiles)
+        if tiles <= 0:
+            tiles = 1 if pack.n_variants * pack.n_genotypes * 4 < (1 << 30) else 4
+        return max(1, min(tiles, max(pack.n_variants, 1)))
+
+    @classmethod
     def _mstep_buffers(cls, pack: DevicePack) -> dict:
         """Output buffers of the (sharded) M-step: two float32 [v_pad, G] tables that alternate as `genotype_addition`
-        (v_pad = V rounded up to the world size, padding rows zero) and the float64 partials of the wide wire format."""
+        (v_pad = V rounded up so that the table splits into equal per-rank slices, padding rows zero), plus, by exchange
+        mode, the peer-mapped partial table or the float64 partials of the wide NCCL wire format.  Collective when
+        sharded (the peer tables are mapped by all ranks together)."""
         dev = pack.device
         world = 1
         if cls.process_group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(cls.process_group)
-        v_pad = -(-max(pack.n_variants, 1) // world) * world
         G = pack.n_genotypes
+        if world > 1 and cls.mstep_exchange in ('auto', 'peer'):
+            import torch.distributed as dist
+            from .distributed import peer_tables
+            if dist.get_backend(cls.process_group) == 'nccl':
+                v_pad = -(-max(pack.n_variants, 1) // (4 * world)) * (4 * world)
+                peer = peer_tables(cls.process_group, dev, v_pad, G)
+                if peer is not None:
+                    return {'v_pad': v_pad, 'world': world, 'tables': peer['tables'], 'peer': peer}
+            assert cls.mstep_exchange == 'auto', 'mstep_exchange = "peer" needs NCCL ranks with symmetric memory'
+        v_pad = -(-max(pack.n_variants, 1) // world) * world
         out = {'v_pad': v_pad, 'world': world,
                'tables': [torch.zeros((v_pad, G), dtype=torch.float32, device=dev) for _ in range(2)]}
         if world > 1 and cls.mstep_allreduce_dtype == 'float64':
-            n_tiles = max(1, int(cls.mstep_allreduce_tiles))
+            n_tiles = cls._allreduce_tiles(pack)
             out['partial64'] = torch.zeros((v_pad, G), dtype=torch.float64, device=dev)
             out['slice64'] = torch.empty((-(-v_pad // n_tiles) + world) * G // world + G, dtype=torch.float64, device=dev)
         return out
@@ -765,7 +791,29 @@ class Demultiplexer:
                 buffers = cls._mstep_buffers(pack)
             if out is None:
                 out = buffers['tables'][0]
-            wide = cls.mstep_allreduce_dtype == 'float64'
+            peer = buffers.get('peer')
+            if peer is not None:
+                # own kernel over NVLink peer memory: local M-step into the peer-mapped partial, barrier, every rank
+                # sums its slice over all partials and stores it into everybody's table, barrier
+                partial, handle = peer['partial'], peer['handles'][0]
+                common = (pack.variant_offsets.data_ptr(), pack.csc_cb.data_ptr(), pack.csc_e.data_ptr(),
+                          singlets.data_ptr(), singlets.shape[1], G, float(cls.contribution_power),
+                          partial.data_ptr(), G, 0, G, 0, V)
+                if plan is None:
+                    _native.check(lib.dmx_mstep(*common, _stream()), 'dmx_mstep')
+                else:
+                    _native.check(lib.dmx_mstep_planned(*common, blob.data_ptr(), pack.n_rows, n_medium,
+                                                        n_heavy_variants, n_heavy_items, scratch.data_ptr(),
+                                                        _stream()), 'dmx_mstep_planned')
+                world = peer['world']
+                ins = (C.c_void_p * world)(*peer['pointers'][partial.data_ptr()])
+                outs = (C.c_void_p * world)(*peer['pointers'][out.data_ptr()])
+                handle.barrier(channel=0, timeout_ms=60_000)
+                _native.check(lib.dmx_peer_sum_f32(ins, outs, peer['rank'], world, partial.numel(), _stream()),
+                              'dmx_peer_sum_f32')
+                handle.barrier(channel=1, timeout_ms=60_000)
+                return out[:V]
+            wide = cls.mstep_allreduce_dtype == 'float6'
             comm = native_comm(cls.process_group, dev)
             if comm is not None:
                 _native.check(lib.dmx_mstep_allreduce(
@@ -773,7 +821,7 @@ class Demultiplexer:
                     singlets.shape[1], G, float(cls.contribution_power), out.data_ptr(),
                     _native.ptr(buffers.get('partial64')) if wide else 0,
                     _native.ptr(buffers.get('slice64')) if wide else 0, V, _native.ptr(blob), pack.n_rows, n_medium,
-                    n_heavy_variants, n_heavy_items, _native.ptr(scratch), comm, int(cls.mstep_allreduce_tiles),
+                    n_heavy_variants, n_heavy_items, _native.ptr(scratch), comm, cls._allreduce_tiles(pack),
                     1 if wide else 0, _stream()), 'dmx_mstep_allreduce')
                 return out[:V]
             # process groups without NCCL (gloo over CUDA tensors): same algebra through torch.distributed

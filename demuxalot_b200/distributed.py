@@ -127,7 +127,44 @@ def native_comm(group, device):
     return _NATIVE_COMMS[key]
 
 
+_PEER_TABLES: dict = {}
+
+
+def peer_tables(group, device, n_rows: int, n_cols: int):
+    """
+    Three float32 [n_rows, n_cols] tables that every rank of `group` has mapped into its address space (torch
+    symmetric memory: CUDA IPC / fabric handles, i.e. NVLink peer memory) -- the M-step partial and the two alternating
+    `genotype_addition` tables that `dmx_peer_sum_f32` reads from / writes to on all ranks.  Collective (every rank must
+    call it with the same shape); cached per shape; None when the platform has no symmetric memory (agreed on by all
+    ranks, `Demultiplexer._m_step` then sums through NCCL).
+    """
+    import torch
+    import torch.distributed as dist
+    key = (id(group), torch.device(device).index, n_rows, n_cols)
+    if key in _PEER_TABLES:
+        return _PEER_TABLES[key]
+    entry, ok = None, 1
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        tensors = [symm_mem.empty((n_rows, n_cols), dtype=torch.float32, device=device) for _ in range(3)]
+        handles = [symm_mem.rendezvous(t, group) for t in tensors]
+        for t in tensors:
+            t.zero_()
+        entry = dict(partial=tensors[0], tables=tensors[1:], handles=handles, rank=dist.get_rank(group),
+                     world=dist.get_world_size(group),
+                     pointers={t.data_ptr(): [int(x) for x in h.buffer_ptrs] for t, h in zip(tensors, handles)})
+    except Exception:  # noqa: BLE001 -- no symmetric memory on this platform / build
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag.item()) == 0:
+        entry = None
+    _PEER_TABLES[key] = entry
+    return entry
+
+
 def release_native_comms() -> None:
+    _PEER_TABLES.clear()
     from . import _native
     lib = _native.load()
     for handle in _NATIVE_COMMS.values():

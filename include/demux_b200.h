@@ -253,6 +253,15 @@ int dmx_route_calls(const int32_t* call_variant, const int32_t* call_cb, const f
  * `addition` (and partial64) must hold v_pad = dmx_mstep_allreduce_padded_variants(n_variants, world) rows of G
  * contiguous floats, rows [n_variants, v_pad) zeroed by the caller once.  plan == NULL: unplanned M-step.
  */
+/* Cross-GPU sum of the M-step partials over peer memory (NVLink / NVSwitch), one kernel, no library collective.
+ * h_partials[r] / h_outputs[r] (HOST arrays of `world` DEVICE pointers): rank r's float32 partial table and output table
+ * as mapped into THIS process (peer mappings: CUDA IPC / fabric handles, e.g. torch symmetric memory).  This rank sums
+ * slice `rank` of the n_elements floats over all partials (rank order, float64, one rounding) and stores the result
+ * into slice `rank` of every output: reduce-scatter + all-gather in one pass, the same bits on every rank.
+ * The caller brackets the call with two cross-rank barriers on `stream`: all partials complete before it, all
+ * outputs complete after it.  n_elements must be a multiple of 4 * world; world <= 16. */
+int dmx_peer_sum_f32(const void* const* h_partials, void* const* h_outputs, int32_t rank, int32_t world,
+                     int64_t n_elements, void* stream);
 int dmx_comm_unique_id(uint8_t* h_id128);
 int dmx_comm_init(const uint8_t* h_id128, int32_t rank, int32_t world, void** h_comm);
 int dmx_comm_destroy(void* comm);

@@ -61,6 +61,12 @@ D.process_group = None
 mbuf, state = D._mstep_buffers(pack), {'k': 0}
 result['em_local_ms'] = timed(lambda: iteration(mbuf, state))
 D.process_group = dist.group.WORLD
+D.mstep_exchange = 'peer'
+mbuf, state = D._mstep_buffers(pack), {'k': 0}
+result['exchange_peer_available'] = 'peer' in mbuf
+if 'peer' in mbuf:
+    result['em_ms/peer (dmx_peer_sum_f32)'] = timed(lambda: iteration(mbuf, state))
+D.mstep_exchange = 'nccl'
 for wire in ('float64', 'float32'):
     for tiles in (1, 2, 4, 8):
         D.mstep_allreduce_dtype, D.mstep_allreduce_tiles = wire, tiles
