@@ -421,6 +421,8 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
         del table, singlets, part_add, column, term, post, addition, pack
     finally:
         D.process_group = None
+    from demuxalot_b200.distributed import release_peer_tables
+    release_peer_tables()
     torch.cuda.empty_cache()
 
     # barcode slice against the oracle, same run: public API on host-regenerated calls (rank 0)
@@ -501,6 +503,8 @@ def run_device_em(ctx: Ctx, D, args, name: str, scale: float, lanes: bool):
         del post, addition, pack
     finally:
         D.process_group = None
+    from demuxalot_b200.distributed import release_peer_tables
+    release_peer_tables()
     torch.cuda.empty_cache()
     if name == 'em_32_3m' and ctx.rank == 0:
         # learnt betas after the EM iterations against the oracle on a barcode slice (bar 1e-5 relative)
@@ -691,8 +695,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             D._m_step(pack, singlets, out=nxt, buffers=mbuf)
             em_state['k'] += 1
         em_ms = ctx.timed(em_iteration, args.warmup, args.steps, flush_buf)
+        # the same iteration without the cross-GPU sum: what the exchange costs (weak-scaling efficiency of the EM loop)
         D.process_group = None
         del mbuf
+        mbuf = D._mstep_buffers(pack)
+        em_local_ms = ctx.timed(em_iteration, 2, max(5, args.steps // 2), flush_buf)
+        del mbuf
+        from demuxalot_b200.distributed import release_peer_tables
+        release_peer_tables()
 
         # end to end through the public API, host inputs (pinned) -> host DataFrames
         # (the synthetic dataset holds millions of small Python objects -- var2varid keys, barcodes; a cyclic-GC pass
@@ -788,6 +798,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                              'profiles/r02_parity_report.json'},
         'em': {'iterations_per_s': args.steps / (em_total_ms / 1e3), 'ms_per_iteration': em_total_ms / args.steps,
                'updates_per_s': units_per_step * args.steps / (em_total_ms / 1e3),
+               'ms_per_iteration_without_exchange': ctx.max(statistics.mean(em_local_ms)),
                'what': 'table + E-step (singlet posteriors) + M-step' + (f' + cross-GPU sum ({em_exchange})' if world > 1 else '')},
     }
     del pack, table, buffers, flush_buf

@@ -163,6 +163,11 @@ def peer_tables(group, device, n_rows: int, n_cols: int):
     return entry
 
 
+def release_peer_tables() -> None:
+    """Drops the cached peer-mapped tables (they are as large as the genotype table: 3 x V x G x 4 bytes)."""
+    _PEER_TABLES.clear()
+
+
 def release_native_comms() -> None:
     _PEER_TABLES.clear()
     from . import _native
