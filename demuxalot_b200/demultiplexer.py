@@ -733,7 +733,8 @@ class Demultiplexer:
         """Output buffers of the (sharded) M-step: two float32 [v_pad, G] tables that alternate as `genotype_addition`
         (v_pad = V rounded up so that the table splits into equal per-rank slices, padding rows zero), plus, by exchange
         mode, the peer-mapped partial table or the float64 partials of the wide NCCL wire format.  Collective when
-        sharded (the peer tables are mapped by all ranks together)."""
+        sharded (the peer tables are mapped by all ranks together).  The CONTENTS of the two tables are unspecified
+        (cached peer tables come back as the previous user left them): callers that read before writing zero them."""
         dev = pack.device
         world = 1
         if cls.process_group is not None:
@@ -1024,6 +1025,11 @@ class Demultiplexer:
         mbuf = cls._mstep_buffers(pack)
         V = pack.n_variants
         addition, spare = mbuf['tables']
+        # genotype_addition starts at zero (demux.py:86).  The peer-mapped tables are cached per shape and REUSED by the
+        # next EM run of the process, still holding that run's sums: without this reset the first E-step of a second
+        # learn_genotypes call would see a stale addition (found by the 8-GPU lanes-vs-oracle check of bench.py).  Every
+        # rank passed the closing barrier of the previous exchange before it gets here, so no peer writes are in flight.
+        addition.zero_()
         table = None
         post = None
         for iteration in range(n_iterations):

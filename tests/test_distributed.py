@@ -193,6 +193,15 @@ def _nccl_worker(rank: int, world: int, port: int, out_dir: str) -> None:
                                                doublet_prior=0.35)
         np.save(os.path.join(out_dir, f'betas_{rank}.npy'), np.array(learnt.get_betas()))
         np.save(os.path.join(out_dir, f'post_{rank}.npy'), post.values)
+        # a different data set of the same table shape in between, then the first call again: the cached peer-mapped
+        # tables are reused and must not leak one run's genotype_addition into the next one's first E-step
+        other = make_dataset(n_genotypes=12, n_snps=1500, n_barcodes=90, rows_per_barcode=40, seed=41, calls_seed=7,
+                             doublet_fraction=0.6)
+        learn_genotypes_sharded(other.calls, other.genotypes, other.barcode_handler, n_iterations=3, doublet_prior=0.35)
+        again, again_post = learn_genotypes_sharded(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4,
+                                                    doublet_prior=0.35)
+        assert np.array_equal(np.array(again.get_betas()), np.array(learnt.get_betas())), 'stale state between EM runs'
+        assert np.array_equal(again_post.values, post.values)
         if rank == 0:
             single, single_post = Demultiplexer.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler,
                                                                 n_iterations=4, doublet_prior=0.35)
