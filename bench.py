@@ -557,6 +557,8 @@ def run_multi_gpu_parity(ctx: Ctx, D):
                                                    doublet_prior=DOUBLET_PRIOR)
         finally:
             D.mstep_exchange, D.mstep_allreduce_dtype = saved
+        ran = D.last_exchange or ''
+        parity_check(ran.startswith(f'{exchange}/{wire}'), f'asked for the {exchange}/{wire} exchange, ran {ran!r}')
         wire = f'{exchange}_{wire}'
         if ctx.rank == 0:
             single, spost = D.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4,
@@ -564,6 +566,7 @@ def run_multi_gpu_parity(ctx: Ctx, D):
             want, opost = O.learn_genotypes(ds.calls, ds.genotypes, ds.barcode_handler, n_iterations=4,
                                             doublet_prior=DOUBLET_PRIOR)
             out[f'sharded_{wire}'] = {
+                'exchange_that_ran': ran,
                 'betas_rel_vs_single_gpu': rel_err(learnt.get_betas(), single.get_betas()),
                 'betas_rel_vs_oracle': rel_err(learnt.get_betas(), want.get_betas()),
                 'posterior_abs_vs_single_gpu': float(np.abs(post.values - spost.values).max()),

@@ -211,6 +211,7 @@ class Demultiplexer:
     #   'nccl': dmx_mstep_allreduce -- NCCL collectives on a second stream, tiled against the M-step kernel
     #   'auto': 'peer' when the platform offers it, else 'nccl'
     mstep_exchange = 'auto'
+    last_exchange: Optional[str] = None  # diagnostic: the exchange the last sharded M-step actually ran
     # tiles of the NCCL path; 0 = by table size: 1 below 1 GiB (every tile costs a launch tail of the M-step tiers, which
     # outweighs what it hides: profiles/r02_sweep_mstep_allreduce_n2.json), 4 above
     mstep_allreduce_tiles = 0
@@ -737,6 +738,8 @@ class Demultiplexer:
         (cached peer tables come back as the previous user left them): callers that read before writing zero them."""
         dev = pack.device
         world = 1
+        assert cls.mstep_exchange in ('auto', 'peer', 'nccl'), f'unknown mstep_exchange {cls.mstep_exchange!r}'
+        assert cls.mstep_allreduce_dtype in ('float32', 'float64'), f'unknown wire dtype {cls.mstep_allreduce_dtype!r}'
         if cls.process_group is not None:
             import torch.distributed as dist
             world = dist.get_world_size(cls.process_group)
@@ -813,8 +816,9 @@ class Demultiplexer:
                 _native.check(lib.dmx_peer_sum_f32(ins, outs, peer['rank'], world, partial.numel(), _stream()),
                               'dmx_peer_sum_f32')
                 handle.barrier(channel=1, timeout_ms=60_000)
+                buffers['last_exchange'] = cls.last_exchange = 'peer/float32'
                 return out[:V]
-            wide = cls.mstep_allreduce_dtype == 'float6'
+            wide = cls.mstep_allreduce_dtype == 'float64'
             comm = native_comm(cls.process_group, dev)
             if comm is not None:
                 _native.check(lib.dmx_mstep_allreduce(
@@ -824,6 +828,8 @@ class Demultiplexer:
                     _native.ptr(buffers.get('slice64')) if wide else 0, V, _native.ptr(blob), pack.n_rows, n_medium,
                     n_heavy_variants, n_heavy_items, _native.ptr(scratch), comm, cls._allreduce_tiles(pack),
                     1 if wide else 0, _stream()), 'dmx_mstep_allreduce')
+                buffers['last_exchange'] = cls.last_exchange = \
+                    f"nccl/{'float64' if wide else 'float32'}/tiles={cls._allreduce_tiles(pack)}"
                 return out[:V]
             # process groups without NCCL (gloo over CUDA tensors): same algebra through torch.distributed
             import torch.distributed as dist
@@ -837,6 +843,7 @@ class Demultiplexer:
                 _native.check(lib.dmx_mstep_planned(*common, blob.data_ptr(), pack.n_rows, n_medium, n_heavy_variants,
                                                     n_heavy_items, scratch.data_ptr(), _stream()), 'dmx_mstep_planned')
             dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=cls.process_group)
+            buffers['last_exchange'] = cls.last_exchange = f"torch.distributed/{'float64' if wide else 'float32'}"
             if wide:
                 _native.check(lib.dmx_round_f64_to_f32(partial.data_ptr(), G, out.data_ptr(), G, V, G, _stream()),
                               'dmx_round_f64_to_f32')

@@ -66,12 +66,15 @@ mbuf, state = D._mstep_buffers(pack), {'k': 0}
 result['exchange_peer_available'] = 'peer' in mbuf
 if 'peer' in mbuf:
     result['em_ms/peer (dmx_peer_sum_f32)'] = timed(lambda: iteration(mbuf, state))
+    assert mbuf.get('last_exchange') == 'peer/float32', mbuf.get('last_exchange')
 D.mstep_exchange = 'nccl'
 for wire in ('float64', 'float32'):
     for tiles in (1, 2, 4, 8):
         D.mstep_allreduce_dtype, D.mstep_allreduce_tiles = wire, tiles
         mbuf, state = D._mstep_buffers(pack), {'k': 0}
-        result[f'em_ms/{wire}/tiles={tiles}'] = timed(lambda: iteration(mbuf, state))
+        ms = timed(lambda: iteration(mbuf, state))
+        result[f'em_ms/{mbuf.get("last_exchange")}'] = ms  # keyed by what RAN, not by what was asked for
+        assert mbuf.get('last_exchange') == f'nccl/{wire}/tiles={tiles}', (mbuf.get('last_exchange'), wire, tiles)
 # plain NCCL collectives on the same buffer, alone
 buf32 = torch.zeros((V, G), dtype=torch.float32, device=dev)
 buf64 = torch.zeros((V, G), dtype=torch.float64, device=dev)

@@ -235,6 +235,31 @@ def _nccl_worker(rank: int, world: int, port: int, out_dir: str) -> None:
             Demultiplexer.mstep_exchange, Demultiplexer.mstep_allreduce_dtype, Demultiplexer.mstep_allreduce_tiles = saved
         np.save(os.path.join(out_dir, f'betas_f32_{rank}.npy'), np.array(narrow.get_betas()))
         np.save(os.path.join(out_dir, f'betas_f64_{rank}.npy'), np.array(wide.get_betas()))
+        # One M-step on the same posteriors under every exchange: the float64 wire must reproduce the single-GPU sums
+        # (rounded once, after the global sum) while float32 partials visibly do not -- a switch that silently does
+        # nothing fails here (it once did: every mode ran the float32 all-reduce and all parity bars still passed).
+        with em_group():
+            shard = Demultiplexer._pack_device(ds.calls, ds.genotypes, 200, add_data_prior=True,
+                                               shard=(rank, world, dist.group.WORLD), keep_calls=False)
+            table = Demultiplexer._probs_table(shard, None, 0.01)
+            _, _, singlets = Demultiplexer._e_step(shard, table, 0.35, want_logits=False, want_post=False,
+                                                   want_singlets=True)
+            for exchange, wire in (('auto', 'float32'), ('nccl', 'float64'), ('nccl', 'float32')):
+                saved = (Demultiplexer.mstep_exchange, Demultiplexer.mstep_allreduce_dtype)
+                Demultiplexer.mstep_exchange, Demultiplexer.mstep_allreduce_dtype = exchange, wire
+                try:
+                    mbuf = Demultiplexer._mstep_buffers(shard)
+                    summed = Demultiplexer._m_step(shard, singlets, out=mbuf['tables'][1], buffers=mbuf).clone()
+                finally:
+                    Demultiplexer.mstep_exchange, Demultiplexer.mstep_allreduce_dtype = saved
+                tag = mbuf['last_exchange'].split('/tiles')[0].replace('/', '_')
+                np.save(os.path.join(out_dir, f'mstep_{tag}_{rank}.npy'), summed.cpu().numpy())
+        if rank == 0:
+            full = Demultiplexer._pack_device(ds.calls, ds.genotypes, 200, add_data_prior=True, keep_calls=False)
+            table = Demultiplexer._probs_table(full, None, 0.01)
+            _, _, singlets = Demultiplexer._e_step(full, table, 0.35, want_logits=False, want_post=False,
+                                                   want_singlets=True)
+            np.save(os.path.join(out_dir, 'mstep_single.npy'), Demultiplexer._m_step(full, singlets).cpu().numpy())
     finally:
         from demuxalot_b200.distributed import release_native_comms
         release_native_comms()
@@ -258,6 +283,19 @@ def test_two_gpu_sharded_em_matches_single_gpu(tmp_path, native_lib):
     assert np.array_equal(n0, n1) and np.allclose(n0, bs, rtol=2e-6, atol=1e-7)
     w0, w1 = np.load(tmp_path / 'betas_f64_0.npy'), np.load(tmp_path / 'betas_f64_1.npy')
     assert np.array_equal(w0, w1) and np.allclose(w0, bs, rtol=1e-6, atol=1e-7) and (w0 == bs).mean() > 0.999
+    # the exchanges on one M-step: every mode ran under its own name (the file names come from what ran), all ranks hold
+    # the same bits, and the wire formats are distinguishable
+    single_sums = np.load(tmp_path / 'mstep_single.npy')
+    touched = single_sums != 0
+    mismatch = {}
+    for tag in ('peer_float32', 'nccl_float64', 'nccl_float32'):
+        a, b = np.load(tmp_path / f'mstep_{tag}_0.npy'), np.load(tmp_path / f'mstep_{tag}_1.npy')
+        assert np.array_equal(a, b), tag
+        assert np.allclose(a, single_sums, rtol=1e-6, atol=0), tag
+        mismatch[tag] = float((a[touched] != single_sums[touched]).mean())
+    assert mismatch['nccl_float64'] < 1e-4, mismatch  # one rounding after the global sum: the bits of one GPU
+    assert mismatch['nccl_float32'] > 10 * mismatch['nccl_float64'] + 1e-3, mismatch  # a rounding per shard shows
+    assert mismatch['peer_float32'] > 10 * mismatch['nccl_float64'] + 1e-3, mismatch
     # against the oracle: learnt betas, the shards' rows and the data prior
     import oracle
     from demuxalot_b200.synthetic import make_dataset
