@@ -354,6 +354,9 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
     t0 = time.perf_counter()
     index = ds.genotypes.hot_path_index()
     t_index = time.perf_counter() - t0
+    # the calls are resident in HBM; the genotype betas are the one host input of this pack (4 GB): pinned, like the
+    # host inputs of the headline's e2e leg (pageable they upload at ~8 GB/s and dominate the pack at N = 8)
+    betas_pinned = pin(ds.genotypes.variant_betas)
     mine = np.arange(ctx.rank, B, ctx.world)
     part = ds.device_calls(mine, ctx.dev)
     ctx.barrier()
@@ -401,6 +404,7 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
             'molecule_calls': int(calls_total), 'read_rows': int(rows_total), 'em_iterations': n_it,
             'host_genotypes_s': round(t_host, 2), 'host_index_s': round(t_index, 2),
             'pack_s': pack_s, 'pack_rows_per_s': rows_total / pack_s, 'pack_stages': pack_stages,
+            'host_betas_pinned': bool(betas_pinned),
             'em_s': em_s, 'ms_per_iteration': 1e3 * em_s / n_it, 'iterations_per_s': n_it / em_s,
             'updates_per_s': rows_total * C * n_it / em_s,
             'what': 'pack = match + histogram + route + all-to-all + sort of the shard (inputs resident in HBM); '
@@ -447,13 +451,14 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
         gl, gp = D.predict_posteriors(calls, ds.genotypes, handler, doublet_prior=DOUBLET_PRIOR)
         t_gpu = time.perf_counter() - t0
         O = oracle.OracleDemultiplexer
-        O.n_jobs = oracle.demux_oracle.default_n_jobs()
-        try:
-            t0 = time.perf_counter()
-            ol, op = O.predict_posteriors(calls, ds.genotypes, handler, doublet_prior=DOUBLET_PRIOR)
-            t_cpu = time.perf_counter() - t0
-        finally:
-            O.n_jobs = 1
+        with all_host_cores():
+            O.n_jobs = n_oracle_cores = oracle.demux_oracle.default_n_jobs()
+            try:
+                t0 = time.perf_counter()
+                ol, op = O.predict_posteriors(calls, ds.genotypes, handler, doublet_prior=DOUBLET_PRIOR)
+                t_cpu = time.perf_counter() - t0
+            finally:
+                O.n_jobs = 1
         # the device generator against its numpy mirror: identical records
         dev_part = ds.device_calls(ids, ctx.dev)
         host_rec = calls['chr1'].snp_calls[:calls['chr1'].n_snp_calls]
@@ -463,9 +468,11 @@ def run_biobank(ctx: Ctx, D, args, scale: float):
             'logits_rel_max': rel_err(gl.values, ol.values, 1e-30), 'posterior_abs_max': float(np.abs(gp.values - op.values).max()),
             'argmax_equal': bool((gp.values.argmax(1) == op.values.argmax(1)).all()),
             'device_generator_equals_host_mirror': same, 'gpu_s': round(t_gpu, 2), 'oracle_s': round(t_cpu, 2),
-            'oracle_cores': oracle.demux_oracle.default_n_jobs()}
+            'oracle_cores': n_oracle_cores}
         parity_check(out['slice_vs_oracle']['logits_rel_max'] <= 1e-5 and same, f"biobank_200 slice vs oracle: {out['slice_vs_oracle']}")
     ctx.barrier()
+    if betas_pinned:
+        unpin(ds.genotypes.variant_betas)
     return out
 
 
@@ -525,11 +532,12 @@ def run_device_em(ctx: Ctx, D, args, name: str, scale: float, lanes: bool):
         handler = BarcodeHandler(ds.barcode_handler.ordered_barcodes[:n_slice])
         learnt, gpost = D.learn_genotypes(calls, ds.genotypes, handler, n_iterations=n_it, doublet_prior=DOUBLET_PRIOR)
         O = oracle.OracleDemultiplexer
-        O.n_jobs = oracle.demux_oracle.default_n_jobs()
-        try:
-            want, opost = O.learn_genotypes(calls, ds.genotypes, handler, n_iterations=n_it, doublet_prior=DOUBLET_PRIOR)
-        finally:
-            O.n_jobs = 1
+        with all_host_cores():
+            O.n_jobs = oracle.demux_oracle.default_n_jobs()
+            try:
+                want, opost = O.learn_genotypes(calls, ds.genotypes, handler, n_iterations=n_it, doublet_prior=DOUBLET_PRIOR)
+            finally:
+                O.n_jobs = 1
         out['slice_vs_oracle'] = {'barcodes': n_slice, 'em_iterations': n_it,
                                   'learnt_betas_rel_max': rel_err(learnt.get_betas(), want.get_betas()),
                                   'posterior_abs_max': float(np.abs(gpost.values - opost.values).max())}
@@ -884,12 +892,36 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         sys.exit(1)
 
 
+ALL_HOST_CORES = None
+
+
+class all_host_cores:
+    """The CPU oracle legs run on rank 0 while the other ranks wait at a barrier: give them every host core back for
+    that time (partition_host_cores otherwise leaves rank 0 with 1 / N of them)."""
+
+    def __enter__(self):
+        self.mine = None
+        if ALL_HOST_CORES:
+            try:
+                self.mine = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, ALL_HOST_CORES)
+            except (AttributeError, OSError):
+                self.mine = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.mine:
+            os.sched_setaffinity(0, self.mine)
+
+
 def partition_host_cores(local_rank: int, local_world: int) -> int:
     """One contiguous block of the host cores per rank (ranks of a node otherwise pile their numpy / gather threads
     onto the same cores, and first-touch puts each rank's buffers on the memory node of the cores it runs on).
     Returns the number of cores of this rank."""
+    global ALL_HOST_CORES
     try:
         cores = sorted(os.sched_getaffinity(0))
+        ALL_HOST_CORES = set(cores)
         per = len(cores) // max(local_world, 1)
         if local_world > 1 and per >= 1:
             os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per])
