@@ -828,9 +828,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 'cold_note': 'first call of the process: pageable host buffers, genotype index not flattened yet '
                              f'(hot_path_index alone: {1e3 * index_s:.0f} ms), device index upload, allocator growth'},
         'gpu_launches': 3 * args.steps,
-        'gpu_launches_note': 'per step: probs_table_vec4_kernel, estep_pairs_warp_kernel, softmax_rows_kernel',
+        'gpu_launches_note': 'per step: probs_table_vec4_kernel, estep_pairs_strip_kernel (row softmax fused for single-item '
+                             'barcodes), softmax_rows_kernel (segment combine + softmax of the multi-item barcodes only)',
         'roofline': {
-            'kernel': 'estep_pairs_warp_kernel', 'bound': 'fp32_pipe', 'achieved': achieved_tflops,
+            'kernel': 'estep_pairs_strip_kernel', 'bound': 'fp32_pipe', 'achieved': achieved_tflops,
             'peak': pipe_peak_tflops, 'unit': 'TFLOP/s', 'frac': achieved_tflops / pipe_peak_tflops,
             'traffic': traffic, 'traffic_source': traffic_source, 'kernel_ms': kernel_s * 1e3,
             'peak_kind': f'{sm_count} SMs x 128 FP32 lane-ops/clk (measured issue rate of FADD2/FMUL2/FADD/FMUL, '

@@ -182,11 +182,15 @@ struct CombineParams {
     int skip_single;  // single-item barcodes were finished (softmax included) by the pair kernel itself
 };
 
-// DMX_ESTEP_AUTO: the reference's roundings wherever the E-step waits on the row stream and they are (nearly) free --
-// singlet columns only, or at most 8 genotypes -- and the product arithmetic for the FP32-bound pair kernels
+// DMX_ESTEP_AUTO: the reference's own roundings for the singlet-only E-step (doublet_prior == 0), the product
+// arithmetic for every kernel with doublet columns.  Measured (profiles/r02_flavours_small.log, r01/r02 parity
+// reports): every posterior that missed the 1e-6 bar under FAST was a doublet_prior == 0 case (13 of 161 in round 1),
+// and EXACT costs 1.3-2.4 x there (0.37 -> 0.89 ms at G = 32, 24 M rows); with doublet columns FAST stayed inside
+// 1e-6 for G <= 8 in every tested case while EXACT costs 2.2 x (G = 4) to 7.1 x (G = 8) on the lane-per-row kernel.
 static inline int resolve_flavour(int flavour, int G, double doublet_prior) {
     if (flavour != DMX_ESTEP_AUTO) return flavour;
-    return (doublet_prior == 0 || G <= 8) ? DMX_ESTEP_EXACT : DMX_ESTEP_FAST;
+    (void)G;
+    return doublet_prior == 0 ? DMX_ESTEP_EXACT : DMX_ESTEP_FAST;
 }
 
 __global__ void __launch_bounds__(128) softmax_rows_kernel(float* __restrict__ logits, int64_t ld_logits, int n_cols,

@@ -702,8 +702,10 @@ static bool patch_kernel_supported(int G) {
 // ---------------------------------------------------------------------------------------------------------------
 // SINGLETS: doublet_prior == 0 -- only the G singlet columns, factor a_g itself (no pair sum, no factor 2).
 // EXACT: the reference's own roundings (demux.py:188-190, 261): p = fl(fl(P_i + P_j) * 0.5), x = fl(fl(p (1 - e)) + e'),
-// t = logf(x), float64 accumulation -- these widths wait on the row stream, so the per-term log costs little, and the
-// float32 logits then carry the reference's rounding noise instead of an independent one (posterior bar 1e-6).
+// t = logf(x), float64 accumulation, so that the float32 logits carry the reference's rounding noise instead of an
+// independent one (posterior bar 1e-6).  Not free: 24 M rows, G = 4: 0.107 -> 0.142 ms (singlets), 0.122 -> 0.267 ms
+// (pairs); G = 8: 0.159 -> 0.247 ms (singlets), 0.214 -> 1.515 ms (pairs: 36 logf and 36 float64 sums per row and
+// lane).  DMX_ESTEP_AUTO picks it for the singlet columns only.
 template <int GT, int FLUSH_ROWS, bool SINGLETS, bool EXACT>
 __global__ void __launch_bounds__(32) estep_pairs_small_kernel(const WarpPairsParams p) {
     constexpr int CT = SINGLETS ? GT : GT * (GT + 1) / 2;

@@ -18,6 +18,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -167,7 +168,8 @@ struct Read {
                 case 'H': {
                     const size_t len = strnlen((const char*)&tags[off], n - off);
                     if (hit) {
-                        if (as_str) as_str->assign((const char*)&tags[off], len);
+                        if (!as_str) return false;  // a text tag where a number was asked for (e.g. AS:Z): not usable
+                        as_str->assign((const char*)&tags[off], len);
                         return true;
                     }
                     off += len + 1;
@@ -185,7 +187,8 @@ struct Read {
                 default: throw Fail{std::string("unknown BAM tag type ") + kind};
             }
             if (hit) {
-                if (as_int) *as_int = value;
+                if (!as_int) return false;  // a numeric tag where text was asked for (e.g. CB:i): `as_str` stays untouched
+                *as_int = value;
                 return kind != 'f';
             }
             off += size;
@@ -199,7 +202,7 @@ bool next_read(Bgzf& in, Read& r, std::vector<uint8_t>& scratch) {
     if (!in.read(&block_size, 4)) return false;
     if (block_size < 32) throw Fail{"corrupt BAM record"};
     scratch.resize((size_t)block_size);
-    in.read(scratch.data(), (size_t)block_size);
+    if (!in.read(scratch.data(), (size_t)block_size)) throw Fail{"truncated BAM (record body missing)"};
     const uint8_t* p = scratch.data();
     int32_t l_seq;
     uint16_t n_cigar;
@@ -521,7 +524,8 @@ dmxio_result* dmxio_count_region(const char* bam_path, int32_t ref_id, uint64_t 
             if (first_open == groups.size()) { groups.clear(); first_open = 0; }
         };
 
-        auto result = new dmxio_result();
+        std::unique_ptr<dmxio_result> owner(new dmxio_result());  // a Fail thrown below must not leak it
+        dmxio_result* const result = owner.get();
         Read read;
         std::vector<uint8_t> scratch;
         std::vector<std::pair<int32_t, Observation>> calls;
@@ -588,7 +592,7 @@ dmxio_result* dmxio_count_region(const char* bam_path, int32_t ref_id, uint64_t 
         result->calls.swap(counter.calls);
         result->n_molecules = counter.n_molecules;
         result->n_calls = counter.n_calls;
-        return result;
+        return owner.release();
     } catch (const Fail& f) {
         g_error = f.what;
         return nullptr;

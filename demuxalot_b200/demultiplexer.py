@@ -187,7 +187,9 @@ class Demultiplexer:
     compensation_during_computing_barcode_logits = 0.5
 
     # B200-specific knobs (not in the reference)
-    estep_flavour = 'auto'  # 'auto' | 'fast' | 'exact', see include/demux_b200.h DMX_ESTEP_*
+    # 'auto' (reference roundings for doublet_prior == 0, product arithmetic with doublet columns) | 'fast' | 'exact',
+    # see include/demux_b200.h DMX_ESTEP_*
+    estep_flavour = 'auto'
     device: Optional[torch.device] = None  # None -> current CUDA device
     process_group = None  # torch.distributed group for barcode-sharded / multi-lane EM (see distributed.py)
     schedule_barcodes = True  # launch the deepest barcodes first (dmx_barcode_schedule)
@@ -310,6 +312,8 @@ class Demultiplexer:
                         try:
                             rc = lib.dmx_host_gather_cb(mols[lo:hi].ctypes.data, hi - lo, base_ptr + 4 * offset, n_threads)
                         finally:
+                            # dmx_last_error() is thread-local: read it on THIS thread, the consumer runs on another
+                            ready_flags[k].msg = lib.dmx_last_error().decode(errors='replace') if rc else ''
                             ready_flags[k].rc = rc
                             ready_flags[k].set()
                         offset += hi - lo
@@ -328,7 +332,8 @@ class Demultiplexer:
                 offset = 0
                 for k, entry in enumerate(uploads):
                     ready_flags[k].wait()
-                    _native.check(ready_flags[k].rc, 'dmx_host_gather_cb')
+                    if ready_flags[k].rc:
+                        raise _native.NativeError(f'dmx_host_gather_cb failed (rc={ready_flags[k].rc}): {ready_flags[k].msg}')
                     lo, hi, per = mol_ranges[k]
                     with torch.cuda.stream(copy_stream):
                         if world > 1:  # equal-sized slices: the tail of the last ones is never read

@@ -31,8 +31,8 @@ extern "C" {
 /* E-step arithmetic flavours (see DESIGN.md "E-step") */
 #define DMX_ESTEP_EXACT 0 /* per-term float32 argument roundings + logf of demux.py:261, float64 accumulation */
 #define DMX_ESTEP_FAST 1  /* a = fma(P, 1-e, e'), products of 8 or 16 row factors, one lg2 per product, float64 accumulation */
-#define DMX_ESTEP_AUTO 2  /* EXACT where the E-step is bound by the row stream (singlet columns only, or <= 8 genotypes),
-                             FAST for the FP32-bound pair kernels (doublet columns, more than 8 genotypes) */
+#define DMX_ESTEP_AUTO 2  /* EXACT for the singlet-only E-step (doublet_prior == 0: the cases where FAST missed the 1e-6
+                             posterior bar; 1.3-2.4 x slower there), FAST whenever there are doublet columns */
 
 /* ---- boundary smoke ------------------------------------------------------------------------------- */
 int dmx_abi_version(void);

@@ -47,9 +47,9 @@ def D(native_lib):
 
 
 def reference_rounding(flavour: str, n_genotypes: int, doublet_prior: float) -> bool:
-    """True when the E-step runs on the reference's own per-term roundings (DMX_ESTEP_EXACT, or DMX_ESTEP_AUTO on the
-    row-stream-bound paths: singlet columns only, or at most 8 genotypes): there the posterior bar is a flat 1e-6."""
-    return flavour == 'exact' or (flavour == 'auto' and (doublet_prior == 0 or n_genotypes <= 8))
+    """True when the E-step runs on the reference's own per-term roundings (DMX_ESTEP_EXACT, or DMX_ESTEP_AUTO for the
+    singlet-only E-step): there the posterior bar is a flat 1e-6."""
+    return flavour == 'exact' or (flavour == 'auto' and doublet_prior == 0)
 
 
 def check_logits_and_posteriors(tag, got_logits, want_logits, got_post, want_post, flat=False):
