@@ -815,6 +815,8 @@ class Demultiplexer:
                                                         n_heavy_variants, n_heavy_items, scratch.data_ptr(),
                                                         _stream()), 'dmx_mstep_planned')
                 world = peer['world']
+                assert out.data_ptr() in peer['pointers'], \
+                    'the sharded M-step writes into one of the peer-mapped tables of _mstep_buffers (pass out=None or one of them)'
                 ins = (C.c_void_p * world)(*peer['pointers'][partial.data_ptr()])
                 outs = (C.c_void_p * world)(*peer['pointers'][out.data_ptr()])
                 handle.barrier(channel=0, timeout_ms=60_000)
