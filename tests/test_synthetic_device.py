@@ -72,3 +72,23 @@ def test_device_generator_equals_host_mirror_and_feeds_the_row_builder(native_li
         assert np.array_equal(bits(pack.csc_e.cpu().numpy()), bits(orows['p_base_wrong']))
         assert np.array_equal(bits(pack.betas.cpu().numpy()), bits(obetas))
     torch.cuda.synchronize()
+
+
+@pytest.mark.gpu
+def test_em_with_detected_snvs_shape_vs_oracle(native_lib):
+    """BASELINE config #3 in miniature: most variants are "detected SNVs" (position known, genotype unknown: zero betas,
+    snp_detection.py:230-242), 10 EM iterations with doublet columns -- learnt betas within 1e-5 relative of the oracle,
+    posteriors within the logit-implied bound, on device-generated calls fed through the public API."""
+    from demuxalot_b200 import Demultiplexer as D
+    from demuxalot_b200.synthetic_device import make_device_dataset
+    ds = make_device_dataset(n_genotypes=32, n_snps=6000, n_barcodes=96, rows_per_barcode=400, seed=20260002,
+                             unknown_genotype_fraction=0.78)
+    calls = ds.host_calls(np.arange(96))
+    assert (np.array(ds.genotypes.get_betas()).sum(axis=1) == 0).mean() > 0.7
+    learnt, post = D.learn_genotypes(calls, ds.genotypes, ds.barcode_handler, n_iterations=10, doublet_prior=0.35)
+    want, want_post = oracle.OracleDemultiplexer.learn_genotypes(calls, ds.genotypes, ds.barcode_handler,
+                                                                 n_iterations=10, doublet_prior=0.35)
+    got, ref = np.array(learnt.get_betas(), np.float64), np.array(want.get_betas(), np.float64)
+    assert (np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)).max() <= 1e-5
+    assert np.abs(post.values - want_post.values).max() <= 1e-5
+    assert (post.values.argmax(axis=1) == want_post.values.argmax(axis=1)).all()
