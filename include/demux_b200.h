@@ -30,7 +30,8 @@ extern "C" {
 
 /* E-step arithmetic flavours (see DESIGN.md "E-step") */
 #define DMX_ESTEP_EXACT 0 /* per-term float32 argument roundings + logf of demux.py:261, float64 accumulation */
-#define DMX_ESTEP_FAST 1  /* a = fma(P, 1-e, e'), products of 8 or 16 row factors, one lg2 per product, float64 accumulation */
+#define DMX_ESTEP_FAST 1  /* a = fma(P, 1-e, e'), float32 products of 8, 16 or 32 row factors with exact exponent
+                             bookkeeping, one lg2 per pair and work item, float64 combination */
 #define DMX_ESTEP_AUTO 2  /* EXACT for the singlet-only E-step (doublet_prior == 0: the cases where FAST missed the 1e-6
                              posterior bar; 1.3-2.4 x slower there), FAST whenever there are doublet columns */
 
@@ -123,7 +124,10 @@ int dmx_probs_from_betas(const float* betas, int64_t ld_betas, const float* addi
  * workspace (query below): float32 [n_barcodes * C] when `logits` is NULL, plus float64 [n_items * C] partial sums
  * when a plan with multi-segment barcodes (n_items > n_barcodes) is given.
  * `table_floor`: a lower bound of the table entries (the clip_lo given to dmx_probs_from_betas), or 0 if
- * unknown; the FAST flavour uses it to decide how many row factors it may multiply before taking one log.
+ * unknown; the FAST flavour uses it to decide how many row factors it may multiply between exponent flushes.
+ * With a plan (dmx_estep_plan) and 25..32 or 57..64 genotypes the row softmax of every barcode that is a single work
+ * item is computed by the E-step kernel itself (no logits round trip through memory); `logits` is then only written
+ * when it is not NULL.  The outputs are the same either way.
  */
 int64_t dmx_estep_workspace_bytes(int64_t n_barcodes, int32_t n_genotypes, double doublet_prior, int64_t n_items,
                                   int32_t need_logits_scratch);
