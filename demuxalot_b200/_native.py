@@ -36,6 +36,7 @@ SIGNATURES = {
     'dmx_barcode_schedule': (C.c_int, [_ptr, _i64, _ptr, _ptr, _i64, _ptr]),
     'dmx_estep': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _ptr, _i64,
                             _ptr, _i64, _ptr, _i64, _i32, _f32, _ptr, _ptr, _i64, _i32, _ptr]),
+    'dmx_estep_strip_layout': (C.c_int, [_i32, _ptr, C.POINTER(_i32)]),
     'dmx_softmax_rows': (C.c_int, [_ptr, _i64, _i64, _i32, _ptr, _i64, _ptr, _i64, _i32, _ptr]),
     'dmx_mstep': (C.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i32, _f64, _ptr, _i64, _ptr, _i64, _i64, _i64, _ptr]),
     'dmx_mstep_plan_bytes': (_i64, [_i64]),

@@ -514,6 +514,24 @@ static bool strip_layout(int nb, StripLayout* out) {
     return true;
 }
 
+}  // namespace dmx
+
+extern "C" int dmx_estep_strip_layout(int32_t n_blocks, int16_t* h_slots, int32_t* h_n_slots) {
+    dmx::StripLayout layout;
+    DMX_REQUIRE(n_blocks == 4 || n_blocks == 8, "the strip kernel serves 4 or 8 blocks of 8 genotypes, not %d", (int)n_blocks);
+    DMX_REQUIRE(dmx::strip_layout(n_blocks, &layout), "no strip layout for %d blocks", (int)n_blocks);
+    const int n_slots = n_blocks == 4 ? 8 : 32;
+    for (int s = 0; s < n_slots; ++s) {
+        const dmx::StripSlot& sl = layout.slot[s];
+        const int16_t fields[8] = {sl.p0, sl.p1, sl.p2, sl.q1, sl.d, sl.P1, sl.P2, 0};
+        for (int k = 0; k < 8; ++k) h_slots[8 * s + k] = fields[k];
+    }
+    *h_n_slots = n_slots;
+    return 0;
+}
+
+namespace dmx {
+
 bool estep_pairs_strip_supported(int G) {
     const char* v = getenv("DMX_PAIRS_STRIP");
     if (v && *v && atoi(v) == 0) return false;

@@ -157,6 +157,13 @@ int dmx_estep_plan(const int64_t* barcode_offsets, const int32_t* barcode_order,
                    int32_t* seg_prefix, int32_t* item_slot, int64_t item_capacity, void* workspace,
                    int64_t workspace_bytes, int64_t* h_n_items, void* stream);
 
+/* Introspection (HOST only, no device work): the assignment of the pair triangle to the lanes of the strip kernel
+ * (csrc/estep_pairs_strip.cu; 25..32 genotypes: n_blocks = 4, 8 slots; 57..64: n_blocks = 8, 32 slots).  h_slots receives 8
+ * int16 per slot: float offsets p0, p1, p2 (pairs of strips 0..2), q1 (block of strips 0, 1), d (block of strip 2 and
+ * unit 3), P1, P2 (pairs of unit 3; P2 < 0: unit 3 is a plain strip), 0.  Lets a CPU test check that every genotype pair is
+ * produced exactly once. */
+int dmx_estep_strip_layout(int32_t n_blocks, int16_t* h_slots, int32_t* h_n_slots);
+
 /* row softmax only (scipy.special.softmax(x, axis=-1), demux.py:101,152); outputs as in dmx_estep */
 int dmx_softmax_rows(const float* logits, int64_t ld_logits, int64_t n_rows, int32_t n_cols,
                      float* posteriors, int64_t ld_post, float* singlet_posteriors, int64_t ld_singlet,

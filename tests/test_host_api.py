@@ -265,3 +265,47 @@ def test_demultiplexer_host_helpers_match_oracle():
             assert option_names(names, dp) == oracle.option_names(names, dp)
             assert len(option_names(names, dp)) == n_options(g, dp)
     assert Demultiplexer.contribution_power == 2. and Demultiplexer.aggregate_on_snps is False
+
+
+@pytest.mark.parametrize('n_blocks', [4, 8])
+def test_strip_kernel_layout_covers_every_pair_exactly_once(native_lib, n_blocks):
+    """Host-side check of csrc/estep_pairs_strip.cu::strip_layout (no GPU): the 36 packed product slots of every lane
+    slot, decoded as the kernel's epilogue decodes them (strip_pair_of), produce every genotype pair i <= j of the padded
+    width exactly once; strips 0, 1 share a block, and the operand loads are aligned as the kernel assumes."""
+    import ctypes as C
+    raw = (C.c_int16 * (32 * 8))()
+    n_slots = C.c_int32(0)
+    assert native_lib.dmx_estep_strip_layout(n_blocks, raw, C.byref(n_slots)) == 0
+    assert n_slots.value == (8 if n_blocks == 4 else 32)
+    G = 8 * n_blocks
+    seen = {}
+    for s in range(n_slots.value):
+        p0, p1, p2, q1, d, P1, P2, _ = raw[8 * s:8 * s + 8]
+        for offset in (p0, p1, p2, P1):
+            assert 0 <= offset < G and offset % 2 == 0  # LDS.64 of a pair
+        assert q1 % 8 == 0 and d % 8 == 0 and 0 <= q1 < G and 0 <= d < G  # LDS.128 of a block
+        assert P2 < 0 or (P2 % 2 == 0 and P2 // 8 == d // 8)
+        for q in range(36):
+            for el in (0, 1):
+                if q < 16:
+                    pair, other = (p0 if q < 8 else p1), q1 + (q & 7)
+                elif q < 24:
+                    pair, other = p2, d + (q & 7)
+                elif q < 32:
+                    pair, other = P1, d + (q & 7)
+                else:
+                    pair, other = P2, d + 4 + (q & 3)
+                if pair < 0:
+                    continue
+                x = pair + el
+                if q >= 24 and pair // 8 == d // 8 and other < x:
+                    continue  # lower triangle of a diagonal block
+                key = (min(x, other), max(x, other))
+                assert key not in seen, (key, seen[key], (s, q, el))
+                seen[key] = (s, q, el)
+    assert set(seen) == {(i, j) for i in range(G) for j in range(i, G)}
+    if n_blocks == 4:  # every slot's unit 3 is a diagonal half whose pairs sit at (2h, 2h+1) / (6-2h, 7-2h) of block d
+        for s in range(8):
+            _, _, _, _, d, P1, P2, _ = raw[8 * s:8 * s + 8]
+            h = (P1 - d) // 2
+            assert h in (0, 1) and P2 - d == (4 if h else 6)
