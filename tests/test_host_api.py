@@ -309,3 +309,24 @@ def test_strip_kernel_layout_covers_every_pair_exactly_once(native_lib, n_blocks
             _, _, _, _, d, P1, P2, _ = raw[8 * s:8 * s + 8]
             h = (P1 - d) // 2
             assert h in (0, 1) and P2 - d == (4 if h else 6)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a shrunken workload: one JSON line with the
+    keys of the bench contract, `value` = resident step, `e2e` = the same plus the pack."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, str(ROOT / 'bench.py'), '--impl', 'reference', '--scale', '0.02', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [line for line in out.stdout.splitlines() if line.startswith('{')]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better',
+                'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert key in line, key
+    assert line['impl'] == 'reference' and line['gpu_launches'] == 0 and line['vs_baseline'] is None
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e']['h2d_bytes_per_step'] == 0 and 0 < line['e2e']['value'] <= line['value']
+    assert 'workload' in line['config']
